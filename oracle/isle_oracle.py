@@ -1,0 +1,426 @@
+"""oracle/isle_oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU restatement (numpy / scipy.sparse) of the reference's spectral core, the
+checker the CUDA path is compared against.  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline leg may import this module; the product path
+(isle_b200/, libisle_cuda.so) never does.
+
+Parity pinning: the reference has no golden vectors of its own,
+so this restatement is pinned against outputs of the UNMODIFIED reference C++
+compiled in-container (oracle/_ref/ref_dump, see oracle/Makefile) on seeded
+corpora; the resulting fixtures live in tests/golden/ together with the script
+that made them (tests/golden/make_golden.py).  The only substitution below the
+reference's C++ is BLAS/LAPACK = OpenBLAS and the MKL sparse calls = plain loops
+(oracle/shim/), which does not touch the bit-exact stages (thresholds, B).
+
+Every function cites the reference file:line it follows (paths relative to the
+reference root).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import scipy.linalg
+import scipy.sparse as sp
+
+F32 = np.float32
+
+
+# --------------------------------------------------------------------------- stage 0
+def normalize_docs(counts, offsets):
+    """src/sparseMatrix.cpp:86-98 (avg_doc_sz, nz_docs) and :136-167 (normalize_docs).
+
+    avg_doc_sz = (float)(total_tokens / nz_docs) with INTEGER division; doc_sum is a
+    sequential fp32 sum of integer-valued floats (exact below 2^24); value =
+    avg_doc_sz * ((float)count / doc_sum) in fp32 with that association.
+    """
+    offsets = np.asarray(offsets, dtype=np.int64)
+    lens = np.diff(offsets)
+    nz_docs = int((lens > 0).sum())
+    total = int(np.asarray(counts, dtype=np.uint64).sum())
+    avg = F32(total // nz_docs)
+    sums = np.zeros(len(lens), dtype=np.int64)
+    nzmask = lens > 0
+    sums[nzmask] = np.add.reduceat(np.asarray(counts, dtype=np.int64), offsets[:-1][nzmask])
+    assert sums.max(initial=0) < (1 << 24)
+    ds = np.repeat(sums.astype(F32), lens)
+    vals = (avg * (np.asarray(counts).astype(F32) / ds)).astype(F32)
+    return vals, avg, nz_docs
+
+
+# --------------------------------------------------------------------------- stage A
+def threshold_counts(nz_docs: int, k: int):
+    """src/sparseMatrix.cpp:370-373: count_gr / count_eq, evaluated in double from
+    (float)nz_docs and (float)k with w0_c=1.0, eps1_c=1.0/60.0 (include/hyperparams.h:8-9)."""
+    w0, eps1 = 1.0, 1.0 / 60.0
+    nzf, kf = float(F32(nz_docs)), float(F32(k))
+    count_gr = int(w0 * nzf / (2.0 * kf))
+    count_eq = int(math.ceil(3.0 * eps1 * w0 * nzf / kf))
+    return max(count_gr, 1), max(count_eq, 1)
+
+
+def round_half_away(x):
+    """std::round on float (src/sparseMatrix.cpp:381,1344): half away from zero."""
+    x = np.asarray(x, dtype=F32)
+    return (np.sign(x) * np.floor(np.abs(x) + F32(0.5))).astype(F32)
+
+
+def compute_thresholds(vals, rows, V: int, nz_docs: int, k: int):
+    """src/sparseMatrix.cpp:289-333 (word-major descending lists) + :357-485 (rank rule).
+
+    Per word w: S_w = rounded values with zeros removed (:378-387).
+      n == 0                -> zeta = 1, kept 0            (:476-480)
+      n <  count_gr         -> zeta = 1, keep all          (:395-412)
+      z = S_w[count_gr-1] (descending); loop (:444-471):
+         eq = #(S_w == z); if eq < count_eq: zeta = z, kept = #(S_w >= z)
+         elif z is the smallest value present or z == 1: zeta = 1, keep all
+         else z = next smaller distinct value
+    Returns (zetas float32[V], new_nnzs).
+    """
+    count_gr, count_eq = threshold_counts(nz_docs, k)
+    r = round_half_away(vals).astype(np.int64)
+    rows = np.asarray(rows, dtype=np.int64)
+    keep = r >= 1
+    r, w = r[keep], rows[keep]
+    maxv = int(r.max(initial=1))
+    hist = np.zeros((V, maxv + 2), dtype=np.int64)
+    np.add.at(hist, (w, r), 1)
+    zetas = np.ones(V, dtype=F32)
+    new_nnzs = 0
+    n_w = hist.sum(1)
+    for word in np.nonzero(n_w)[0]:
+        h = hist[word]
+        n = int(n_w[word])
+        if n < count_gr:
+            new_nnzs += n
+            continue
+        vals_present = np.nonzero(h)[0][::-1]  # descending distinct values
+        cum = np.cumsum(h[vals_present])       # #(>= value)
+        i = int(np.searchsorted(cum, count_gr, side="left"))  # count_gr-th largest
+        while True:
+            z = int(vals_present[i])
+            if h[z] < count_eq:
+                zetas[word] = F32(z)
+                new_nnzs += int(cum[i])
+                break
+            if i == len(vals_present) - 1 or z == 1:
+                zetas[word] = F32(1.0)
+                new_nnzs += n
+                break
+            i += 1
+    return zetas, int(new_nnzs)
+
+
+# --------------------------------------------------------------------------- stage B
+def sampling_weights(vals, rows, offsets, zetas):
+    """src/sparseMatrix.cpp:1383-1397: weight_d = sum of zeta_w over kept entries (fp32)."""
+    r = round_half_away(vals)
+    z = np.asarray(zetas, dtype=F32)[np.asarray(rows, dtype=np.int64)]
+    contrib = np.where(r >= z, z, F32(0)).astype(np.float64)
+    cs = np.concatenate([[0.0], np.cumsum(contrib)])
+    offsets = np.asarray(offsets, dtype=np.int64)
+    return (cs[offsets[1:]] - cs[offsets[:-1]]).astype(F32)
+
+
+def threshold_and_copy(vals, rows, offsets, zetas, select_docs=None):
+    """src/sparseMatrix.cpp:1285-1361 (threshold_and_copy / _doc_block); with a mask it is
+    the tail of sampled_threshold_and_copy (:1417-1430).
+
+    Entry kept iff round(val) >= zeta[row]; stored value sqrtf(zeta[row]) (:1344-1349);
+    docs with no kept entry are dropped and ids compacted, original_cols[new] = old (:1355-1359).
+    Returns (B_vals f32, B_rows u32, B_offsets i64, original_cols u32).
+    """
+    offsets = np.asarray(offsets, dtype=np.int64)
+    rows = np.asarray(rows, dtype=np.int64)
+    z = np.asarray(zetas, dtype=F32)[rows]
+    keep = round_half_away(vals) >= z
+    D = len(offsets) - 1
+    doc_of = np.repeat(np.arange(D, dtype=np.int64), np.diff(offsets))
+    if select_docs is not None:
+        keep &= np.asarray(select_docs, dtype=bool)[doc_of]
+    kept_per_doc = np.bincount(doc_of[keep], minlength=D)
+    nonempty = kept_per_doc > 0
+    original_cols = np.nonzero(nonempty)[0].astype(np.uint32)
+    b_offsets = np.zeros(len(original_cols) + 1, dtype=np.int64)
+    np.cumsum(kept_per_doc[nonempty], out=b_offsets[1:])
+    b_rows = rows[keep].astype(np.uint32)
+    b_vals = np.sqrt(z[keep]).astype(F32)
+    return b_vals, b_rows, b_offsets, original_cols
+
+
+def to_csc(b_vals, b_rows, b_offsets, V):
+    D = len(b_offsets) - 1
+    return sp.csc_matrix((np.asarray(b_vals, dtype=F32), np.asarray(b_rows, dtype=np.int64),
+                          np.asarray(b_offsets, dtype=np.int64)), shape=(V, D))
+
+
+# --------------------------------------------------------------------------- stage C
+def spsptr_multiply(B_csc, X):
+    """include/matUtils.h:336-365 MKL_SpSpTrProd::multiply: Z = B (B^T X), fp32."""
+    Y = (B_csc.T @ X.astype(F32)).astype(F32)
+    return (B_csc @ Y).astype(F32)
+
+
+def compute_qr(A):
+    """block-ks/ks_utils.h:43-127: rank-revealing MGS with one re-orthogonalisation, in
+    fp64; v_norm is rounded to float (:66 ARMA_FPTYPE); columns with norm < 1e-6 dropped.
+    Returns (Q f32 [n x r], R f32 [r x b], rank)."""
+    a = np.array(A, dtype=np.float64)
+    n, b = a.shape
+    Q = np.zeros((n, b))
+    R = np.zeros((b, b))
+    rank = 0
+    for i in range(b):
+        v = a[:, i].copy()
+        v_norm = float(F32(math.sqrt(float(v @ v))))
+        if v_norm < 1e-6:
+            continue
+        q = v / v_norm
+        Q[:, rank] = q
+        bb = q @ a[:, i:]
+        a[:, i:] -= np.outer(q, bb)
+        cc = q @ a[:, i:]
+        a[:, i:] -= np.outer(q, cc)
+        R[rank, i:] = bb + cc
+        rank += 1
+    return Q[:, :rank].astype(F32), R[:rank].astype(F32), rank
+
+
+class BlockKS:
+    """block-ks/restarted_block_ks.h restated.  `op(X)` multiplies an
+    n x b fp32 block.  RNG is numpy (the reference uses libc rand()): parity is
+    by invariant subspace, never by RNG replay."""
+
+    def __init__(self, op, n, nev, ncv=None, maxit=100, blk=10, tol=1e-4, seed=0):
+        self.op, self.n, self.nev = op, n, nev
+        self.blk = blk if blk < nev else 1          # restarted_block_ks.h:198
+        self.ncv = ncv if ncv is not None else 2 * nev + blk
+        self.maxit, self.tol = maxit, F32(tol)
+        self.rng = np.random.Generator(np.random.PCG64(seed))
+        self.nconv = 0
+        self.n_op = 0
+        self.n_restarts = 0
+
+    def _randu(self, n, m):
+        return self.rng.random((n, m), dtype=F32)
+
+    def init(self):
+        """restarted_block_ks.h:204-259."""
+        b = self.blk
+        while True:
+            Q, R, rank = compute_qr(self._randu(self.n, b))
+            if rank == b:
+                break
+        V = Q
+        V1 = self.op(V); self.n_op += 1
+        H = (V.T @ V1).astype(F32)
+        V1 = V1 - V @ H
+        C = (V.T @ V1).astype(F32)
+        H = H + C
+        V1 = V1 - V @ C
+        Q, R, rank = compute_qr(V1)
+        R = np.vstack([R, np.zeros((b - rank, b), dtype=F32)])
+        self.H = np.vstack([H, R]).astype(F32)
+        V = np.hstack([V, Q])
+        if rank < b:
+            V = self._refill(V, V.shape[1], 2 * b)
+        self.V = V.astype(F32)
+
+    def _refill(self, V, nvecs, target):
+        """rank-deficiency fix, restarted_block_ks.h:106-131 / :238-258."""
+        tries = 0
+        if V.shape[1] < target:
+            V = np.hstack([V, np.zeros((self.n, target - V.shape[1]), dtype=F32)])
+        while nvecs < target and tries < 100:
+            tries += 1
+            F2 = self._randu(self.n, target - nvecs)
+            W = V[:, :nvecs]
+            F2 = F2 - W @ (W.T @ F2)
+            F2 = F2 - W @ (W.T @ F2)
+            Q2, _, rk2 = compute_qr(F2)
+            if rk2 > 0:
+                V[:, nvecs:nvecs + rk2] = Q2
+                nvecs += rk2
+        return V
+
+    def expand(self):
+        """restarted_block_ks.h:63-136."""
+        b, ncv = self.blk, self.ncv
+        V, H = self.V, self.H
+        V = np.hstack([V, np.zeros((self.n, ncv - H.shape[0]), dtype=F32)])
+        while H.shape[0] < ncv:
+            rows, cols = H.shape
+            Vk = V[:, cols:rows]
+            F = self.op(Vk); self.n_op += 1
+            W = V[:, :rows]
+            Hk = (W.T @ F).astype(F32)
+            F = (F - W @ Hk).astype(F32)
+            for _ in range(2):
+                Ck = (W.T @ F).astype(F32)
+                F = (F - W @ Ck).astype(F32)
+                Hk = Hk + Ck
+            H = np.hstack([H, Hk])
+            H = np.vstack([H, np.zeros((b, H.shape[1]), dtype=F32)])
+            Q, R, rk = compute_qr(F)
+            V[:, H.shape[1]:H.shape[1] + rk] = Q
+            R = np.vstack([R, np.zeros((b - rk, b), dtype=F32)])
+            H[H.shape[0] - b:, H.shape[1] - b:] = R
+            if rk < b:
+                V = self._refill(V, H.shape[1] + rk, H.shape[0])
+        self.V, self.H = V, H
+
+    def truncate(self):
+        """restarted_block_ks.h:139-187.  eig_sym -> ssyevd with uplo='U'
+        (armadillo_bits/auxlib_meat.hpp:1670-1682): only the upper triangle of H is read."""
+        b, nev, nconv = self.blk, self.nev, self.nconv
+        V, H = self.V, self.H
+        m = H.shape[1]
+        subH = H[nconv:m, nconv:m]
+        eH, vH = scipy.linalg.eigh(subH.astype(F32), lower=False)
+        idx = np.argsort(-eH, kind="stable")
+        eH, vH = eH[idx].astype(F32), vH[:, idx].astype(F32)
+        new_starts = V[:, -b:]
+        preserve = V[:, :nconv]
+        mid = (V[:, nconv:V.shape[1] - b] @ vH[:, :nev - nconv]).astype(F32)
+        V = np.hstack([preserve, mid, new_starts])
+        H = H.copy()
+        H[nconv:nev, nconv:nev] = np.diag(eH[:nev - nconv])
+        H[nev:nev + b, nconv:m] = H[H.shape[0] - b:, m - b:m] @ vH[-b:, :]
+        if nconv > 0:
+            H[:nconv, nconv:m] = H[:nconv, nconv:m] @ vH
+        self.V, self.H = V.astype(F32), H[:nev + b, :nev].astype(F32)
+
+    def compute(self):
+        """restarted_block_ks.h:262-321."""
+        self.nconv = 0
+        self.expand()
+        while self.n_restarts < self.maxit:
+            self.truncate()
+            res = self.H[-self.blk:, :]
+            norms = np.sqrt((res.astype(F32) ** 2).sum(0)).astype(F32)
+            evs = np.diag(self.H)[:norms.size]
+            norms = norms / evs
+            bad = np.nonzero(norms >= self.tol)[0]
+            if bad.size == 0:
+                self.nconv = norms.size
+                break
+            self.nconv = int(bad[0])
+            self.n_restarts += 1
+            self.expand()
+        self.nconv = min(self.nconv, self.nev)
+        return self.nconv
+
+    def eigenvalues(self):
+        return np.diag(self.H)[: self.nev].astype(F32)
+
+    def eigenvectors(self):
+        return self.V[:, : self.nev].astype(F32)
+
+
+def block_ks(B_csc, k, blk=10, maxit=100, tol=1e-4, seed=0):
+    """src/sparseMatrix.cpp:1195-1220 compute_block_ks: evalues (sigma^2, descending), U (V x k)."""
+    ks = BlockKS(lambda X: spsptr_multiply(B_csc, X), B_csc.shape[0], k, 2 * k + blk, maxit, blk, tol, seed)
+    ks.init()
+    nconv = ks.compute()
+    return ks.eigenvalues(), ks.eigenvectors(), nconv, ks
+
+
+# --------------------------------------------------------------------------- stages D/E
+def project(B_csc, U):
+    """src/sparseMatrix.cpp:1749-1791 multiply_with/UT_times_docs: P = B^T U (docs x k), fp32."""
+    return np.asarray(B_csc.T @ U.astype(F32), dtype=F32)
+
+
+def docs_l2sq(P):
+    """src/sparseMatrix.cpp:1888-1918 compute_projected_docs_l2sq."""
+    return np.einsum("ij,ij->i", P, P, dtype=F32).astype(F32)
+
+
+def dist_matrix(P, d2, C):
+    """src/sparseMatrix.cpp:1794-1849: ((-2 P C^T) + ||c||^2) + ||d||^2 in fp32, that order."""
+    c2 = np.einsum("ij,ij->i", C, C, dtype=F32).astype(F32)
+    G = (F32(-2.0) * (P @ C.T.astype(F32))).astype(F32)
+    return ((G + c2[None, :]).astype(F32) + d2[:, None]).astype(F32)
+
+
+def closest_centers(P, d2, C):
+    """src/sparseMatrix.cpp:1852-1871: cblas_isamin = first index of min |x|."""
+    return np.argmin(np.abs(dist_matrix(P, d2, C)), axis=1).astype(np.uint32)
+
+
+def lloyds_iter(P, d2, C):
+    """src/sparseMatrix.cpp:1921-2013: assign, then centers = mean of members; an empty
+    cluster's center is left at zero (:1988-1992).  Returns (new C, assignment)."""
+    k = C.shape[0]
+    a = closest_centers(P, d2, C)
+    newC = np.zeros_like(C, dtype=np.float64)
+    np.add.at(newC, a, P.astype(np.float64))
+    cnt = np.bincount(a, minlength=k)
+    nz = cnt > 0
+    newC[nz] /= cnt[nz][:, None]
+    return newC.astype(F32), a
+
+
+def run_lloyds(P, C0, max_reps=10):
+    """src/sparseMatrix.cpp:2016-2072: stop when the partition equals the previous one."""
+    d2 = docs_l2sq(P)
+    C = C0.astype(F32).copy()
+    prev = None
+    a = None
+    iters = 0
+    for _ in range(max_reps):
+        C, a = lloyds_iter(P, d2, C)
+        iters += 1
+        if prev is not None and np.array_equal(prev, a):
+            break
+        prev = a
+    return C, a, iters
+
+
+def kmeans_objective(P, C, a):
+    """Harness-side objective sum_d ||P_d - c_a(d)||^2 in fp64 (the reference never computes
+    one: SURVEY Q13); used identically for both sides of the parity check."""
+    diff = P.astype(np.float64) - C.astype(np.float64)[a]
+    return float((diff * diff).sum())
+
+
+def kmeanspp(P, k, rng):
+    """src/sparseMatrix.cpp:2133-2209: D^2 sampling with batched draws (1 + sqrt(max(s-5,0))
+    new centers per distance refresh); clamp >= 0 (:2116,2122); fp32 serial prefix sum
+    (:2170-2172); center = upper_bound(cumul, t) - 1; duplicates skipped (:2190)."""
+    D = P.shape[0]
+    d2 = docs_l2sq(P)
+    centers = [int(rng.integers(0, D))]
+    min_dist = np.full(D, np.finfo(F32).max, dtype=F32)
+    new_added = 1
+    while len(centers) < k:
+        Cn = P[centers[len(centers) - new_added:]]
+        dm = np.maximum(dist_matrix(P, d2, Cn), F32(0))
+        min_dist = np.minimum(min_dist, dm.min(1)).astype(F32)
+        cumul = np.concatenate([[F32(0)], np.cumsum(min_dist, dtype=F32)])
+        s = len(centers)
+        new_added = 0
+        c = 0
+        while c < 1 + math.sqrt(max(s - 5, 0)) and len(centers) < k:
+            t = float(cumul[-1]) * rng.random()
+            nc = int(np.searchsorted(cumul, t, side="right") - 1)
+            if nc not in centers and nc < D:
+                centers.append(nc)
+                new_added += 1
+            c += 1
+    return np.array(centers, dtype=np.int64), P[centers].astype(F32)
+
+
+def lift_centers(U, C_lowd):
+    """src/sparseMatrix.cpp:1438-1450 left_multiply_by_U_Spectra: centers (V x k) = U C^T."""
+    return (U.astype(F32) @ C_lowd.T.astype(F32)).astype(F32)
+
+
+# --------------------------------------------------------------------------- comparisons
+def principal_angle_sin(U1, U2):
+    """sin of the largest principal angle between span(U1) and span(U2) (orthonormal cols)."""
+    Q1, _ = np.linalg.qr(U1.astype(np.float64))
+    Q2, _ = np.linalg.qr(U2.astype(np.float64))
+    R = Q2 - Q1 @ (Q1.T @ Q2)
+    return float(np.linalg.norm(R, 2))

@@ -1,0 +1,86 @@
+"""Regenerates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/ref_dump).
+
+Runs only in the build container (needs /root/reference to have been compiled by
+`make -C oracle`).  The GPU box and the CPU test-suite consume the committed .npz
+files; nothing under tests/ reads /root/reference at run time.
+
+    python tests/golden/make_golden.py
+
+tiny : full arrays (corpus, zetas, B, evalues, U, seeds, Lloyd in/out)
+c1   : BASELINE.json configs[0] shape (10k docs x 5k vocab, k=20): zetas, evalues,
+       Lloyd in/out in full; corpus and B by SHA-256 digest (regenerated from the seed).
+"""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, ROOT)
+from isle_b200 import corpus  # noqa: E402
+
+
+def sha(*arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def run(name, extra=()):
+    c = corpus.generate(name)
+    tmp = tempfile.mkdtemp(prefix=f"isle_golden_{name}_")
+    c.write_bin(os.path.join(tmp, "corpus.bin"))
+    env = dict(os.environ, OMP_THREAD_LIMIT=str(os.cpu_count()))
+    subprocess.run([os.path.join(ROOT, "oracle/_ref/ref_dump"), os.path.join(tmp, "corpus.bin"), tmp,
+                    str(c.k), *extra], check=True, env=env, stdout=subprocess.DEVNULL)
+    meta = json.load(open(os.path.join(tmp, "meta.json")))
+    ld = lambda n, dt: np.fromfile(os.path.join(tmp, n + ".bin"), dtype=dt)
+    out = dict(
+        V=c.V, D=c.D, k=c.k, nnz=c.nnz,
+        avg_doc_sz=ld("A_avg_doc_sz", np.float32)[0],
+        new_nnzs=meta["new_nnzs"], D_B=meta["D_B"], nnz_B=meta["nnz_B"], frobenius=meta["frobenius"],
+        zetas=ld("zetas", np.float32),
+        evalues=ld("evalues", np.float32),
+        U_colmajor=ld("U_colmajor", np.float32),
+        seeds=ld("seeds", np.uint64),
+        centers_lowd_init=ld("centers_lowd_init", np.float32),
+        centers_lowd_final=ld("centers_lowd_final", np.float32),
+        lloyd_assign=ld("lloyd_assign", np.uint32),
+        corpus_sha=sha(c.offsets, c.rows, c.counts),
+        A_vals_sha=sha(ld("A_normalized_vals", np.float32)),
+        B_sha=sha(ld("B_vals", np.float32), ld("B_rows", np.uint64).astype(np.uint32),
+                  ld("B_offsets", np.int64), ld("B_original_cols", np.uint64).astype(np.uint32)),
+    )
+    return c, tmp, out, ld
+
+
+if __name__ == "__main__":
+    here = os.path.dirname(__file__)
+    c, tmp, out, ld = run("tiny")
+    out.update(offsets=c.offsets, rows=c.rows, counts=c.counts,
+               A_normalized_vals=ld("A_normalized_vals", np.float32),
+               B_vals=ld("B_vals", np.float32), B_rows=ld("B_rows", np.uint64).astype(np.uint32),
+               B_offsets=ld("B_offsets", np.int64),
+               B_original_cols=ld("B_original_cols", np.uint64).astype(np.uint32))
+    np.savez_compressed(os.path.join(here, "tiny.npz"), **out)
+
+    # same corpus with an injected doc-selection mask (sampled_threshold_and_copy path)
+    rng = np.random.Generator(np.random.PCG64(7))
+    mask = (rng.random(c.D) < 0.4).astype(np.uint8)
+    mpath = os.path.join(tmp, "mask.u8")
+    mask.tofile(mpath)
+    subprocess.run([os.path.join(ROOT, "oracle/_ref/ref_dump"), os.path.join(tmp, "corpus.bin"), tmp,
+                    str(c.k), "--upto", "B", "--mask", mpath], check=True, stdout=subprocess.DEVNULL)
+    np.savez_compressed(os.path.join(here, "tiny_masked.npz"), mask=mask,
+                        B_vals=ld("B_vals", np.float32), B_rows=ld("B_rows", np.uint64).astype(np.uint32),
+                        B_offsets=ld("B_offsets", np.int64),
+                        B_original_cols=ld("B_original_cols", np.uint64).astype(np.uint32))
+
+    c, tmp, out, ld = run("c1")
+    np.savez_compressed(os.path.join(here, "c1.npz"), **out)
+    print("golden fixtures written:", os.listdir(here))
