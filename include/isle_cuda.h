@@ -1,0 +1,149 @@
+/*
+ * isle_cuda.h -- C ABI of libisle_cuda.so: the B200 (sm_100a) spectral core of ISLETrain.
+ *
+ * The reference (microsoft/ISLE) has no plugin/FFI layer; its spectral core is a set of
+ * member functions of ISLE::SparseMatrix<float> / ISLE::FPSparseMatrix<float>
+ * (reference include/sparseMatrix.h) called in a fixed order by ISLETrainer::train()
+ * (reference src/trainer.cpp:430-554).  Each entry point below replaces one of those
+ * members; the replacement translation unit that forwards the C++ members to this ABI is
+ * isle_b200/shim/sparseMatrix_cuda.cpp.  Plain pointers and sizes
+ * only; every host array is borrowed for the duration of the call; device memory is owned
+ * by the context.  All functions return 0 on success and a non-zero code otherwise, with a
+ * message available from isle_cuda_last_error().  One caller thread per context
+ * (train() is single-threaded).
+ *
+ * Index widths follow the reference build (-DMKL_ILP64: word_id_t/doc_id_t = uint64_t,
+ * offset_t = int64_t, reference include/types.h:24-26); they are narrowed to u32 on upload.
+ */
+#ifndef ISLE_CUDA_H
+#define ISLE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct isle_cuda_ctx isle_cuda_ctx;
+
+enum {
+    ISLE_OK = 0,
+    ISLE_ERR_CUDA = 1,      /* CUDA / cuBLAS / cuSOLVER / NCCL runtime failure            */
+    ISLE_ERR_ARG = 2,       /* invalid argument or call order                               */
+    ISLE_ERR_RANGE = 3,     /* input violates a reference invariant (e.g. value > avg size) */
+    ISLE_ERR_NOCONV = 4,    /* eigensolver did not converge all k pairs                     */
+    ISLE_ERR_NOGPU = 5      /* no usable sm_100 device: there is NO CPU fallback            */
+};
+
+/* ---- lifetime -------------------------------------------------------------------- */
+/* Single-GPU context on CUDA device `device`. */
+int isle_cuda_create(isle_cuda_ctx **ctx, int device);
+/* Document-sharded context: rank `rank` of `world` ranks (one process per GPU).  `nccl_id`
+ * is the 128-byte ncclUniqueId produced by isle_cuda_nccl_unique_id() on rank 0 and
+ * broadcast by the host (torch.distributed / MPI / files).  Each rank later uploads its
+ * contiguous slice of documents; V, k and all outputs are global. */
+int isle_cuda_create_sharded(isle_cuda_ctx **ctx, int device, int rank, int world,
+                             const void *nccl_id);
+int isle_cuda_nccl_unique_id(void *id128);
+void isle_cuda_destroy(isle_cuda_ctx *ctx);
+const char *isle_cuda_last_error(const isle_cuda_ctx *ctx);
+
+/* ---- stage A/B: thresholds and the thresholded matrix B -------------------------- */
+/* Upload the normalised doc-major CSC of A (reference SparseMatrix<float>:
+ * normalized_vals_CSC / rows_CSC / offsets_CSC, include/sparseMatrix.h:23-38) together with
+ * avg_doc_sz and the number of non-empty docs (src/sparseMatrix.cpp:97-98).
+ * In a sharded context D/nnz/arrays describe the local slice, nz_docs the local count. */
+int isle_cuda_upload_A(isle_cuda_ctx *ctx, uint64_t V, uint64_t D, int64_t nnz,
+                       const float *normalized_vals, const uint64_t *rows,
+                       const int64_t *offsets, float avg_doc_sz, uint64_t nz_docs);
+/* Same with 32-bit row ids (harness convenience; no reference counterpart). */
+int isle_cuda_upload_A_u32(isle_cuda_ctx *ctx, uint64_t V, uint64_t D, int64_t nnz,
+                           const float *normalized_vals, const uint32_t *rows,
+                           const int64_t *offsets, float avg_doc_sz, uint64_t nz_docs);
+/* Replaces list_word_freqs_by_sorting + compute_thresholds
+ * (src/sparseMatrix.cpp:289-333, 357-485).  zetas_out: V floats; *new_nnz_out = number of
+ * entries with round(value) >= zeta (the function's return value). */
+int isle_cuda_thresholds(isle_cuda_ctx *ctx, uint64_t k, float *zetas_out,
+                         int64_t *new_nnz_out);
+/* Replaces threshold_and_copy (src/sparseMatrix.cpp:1285-1361); with a non-NULL
+ * select_docs[D] mask it is the tail of sampled_threshold_and_copy (:1417-1430) for that
+ * selection.  B stays on the device. */
+int isle_cuda_build_B(isle_cuda_ctx *ctx, const uint8_t *select_docs_or_null,
+                      int64_t *nnz_B_out, uint64_t *D_B_out);
+/* Per-document importance-sampling weights, sum of zeta_w over kept entries
+ * (src/sparseMatrix.cpp:1383-1397); weights_out: D floats. */
+int isle_cuda_sampling_weights(isle_cuda_ctx *ctx, float *weights_out);
+/* Copies B back in the reference's layout for the host stages that follow the spectral
+ * core (vals f32[nnz_B], rows u64[nnz_B], offsets i64[D_B+1], original_cols u64[D_B]).
+ * Any pointer may be NULL to skip that array. */
+int isle_cuda_download_B(isle_cuda_ctx *ctx, float *vals, uint64_t *rows, int64_t *offsets,
+                         uint64_t *original_cols);
+/* FPSparseMatrix::frobenius (src/sparseMatrix.cpp:1096-1100): sum of squares of B. */
+int isle_cuda_frobenius(isle_cuda_ctx *ctx, float *out);
+
+/* ---- stage C: top-k eigenpairs of B B^T ------------------------------------------ */
+/* MKL_SpSpTrProd::multiply (include/matUtils.h:336-365): Z = B (B^T X) for a V x b
+ * column-major block (b <= 16).  Exposed so the operator can be checked on its own. */
+int isle_cuda_spsptr_multiply(isle_cuda_ctx *ctx, int b, const float *X_colmajor,
+                              float *Z_colmajor);
+/* Replaces initialize_for_eigensolver + compute_block_ks (src/sparseMatrix.cpp:1150-1158,
+ * 1195-1220): restarted block Krylov-Schur, nev=k, ncv=2k+b (block-ks/restarted_block_ks.h).
+ * evalues_out: k floats (sigma^2, descending); U_colmajor_out: V*k floats or NULL;
+ * *nconv_out = converged pairs.  Returns ISLE_ERR_NOCONV when nconv != k (the reference
+ * asserts, src/sparseMatrix.cpp:1207); outputs are still filled. */
+int isle_cuda_block_ks(isle_cuda_ctx *ctx, uint64_t k, int b, int max_restarts, float tol,
+                       uint64_t seed, float *evalues_out, float *U_colmajor_out,
+                       int *nconv_out);
+/* Harness hook: install an externally computed U (V x k column-major) so that the k-means
+ * stages can be checked on an identical projection. */
+int isle_cuda_set_U(isle_cuda_ctx *ctx, uint64_t k, const float *U_colmajor);
+
+/* ---- stage D/E: k-means on the rank-k projection ---------------------------------- */
+/* Materialises P = B^T U (D_B x k) on the device; P_out (row-major, D_B*k floats) and
+ * l2sq_out (D_B floats, compute_projected_docs_l2sq, src/sparseMatrix.cpp:1888-1918) may
+ * be NULL.  Called implicitly by the k-means entry points when needed. */
+int isle_cuda_project(isle_cuda_ctx *ctx, float *P_out, float *l2sq_out);
+/* Replaces kmeans_init_on_projected_space / kmeanspp_on_projected_space
+ * (src/sparseMatrix.cpp:2133-2238).  seeds_out: k doc ids (B numbering);
+ * centers_lowd_out: k*k floats, center c at [c*k, (c+1)*k). */
+int isle_cuda_kmeanspp(isle_cuda_ctx *ctx, uint64_t k, uint64_t seed, uint64_t *seeds_out,
+                       float *centers_lowd_out, float *residual_out);
+/* Replaces run_lloyds_on_projected_space (src/sparseMatrix.cpp:1921-2072).
+ * assign_out (D_B u32, may be NULL) is the final partition; *objective_out (may be NULL)
+ * = sum_d ||P_d - c_assign(d)||^2 in fp64 for the returned centers/partition;
+ * *iters_out (may be NULL) = Lloyd iterations executed. */
+int isle_cuda_lloyd_projected(isle_cuda_ctx *ctx, uint64_t k, float *centers_lowd_inout,
+                              int max_reps, uint32_t *assign_out, double *objective_out,
+                              int *iters_out);
+/* One assignment pass only (projected_closest_centers, src/sparseMatrix.cpp:1852-1871):
+ * argmin_c | ||d||^2 + ||c||^2 - 2 d.c |, first index on ties (cblas_isamin). */
+int isle_cuda_assign_projected(isle_cuda_ctx *ctx, uint64_t k, const float *centers_lowd,
+                               uint32_t *assign_out);
+/* Replaces left_multiply_by_U_Spectra (src/sparseMatrix.cpp:1438-1450):
+ * centers_out (V x ncols, column-major) = U * in (k x ncols column-major, leading dim ld_in). */
+int isle_cuda_lift_centers(isle_cuda_ctx *ctx, uint64_t ncols, const float *in, uint64_t ld_in,
+                           float *centers_out);
+/* cleanup_after_eigensolver (src/sparseMatrix.cpp:1264-1275): frees U, P and solver state. */
+int isle_cuda_cleanup_eigensolver(isle_cuda_ctx *ctx);
+
+/* ---- measurement ------------------------------------------------------------------ */
+/* Turn per-kernel CUDA-event timing on/off (off by default; events are recorded on the
+ * context's own stream around each launch of the named kernel families). */
+int isle_cuda_set_profiling(isle_cuda_ctx *ctx, int enabled);
+/* Named counters, e.g. "launches", "spmm_bt_ms", "spmm_bt_calls", "spmm_bt_bytes",
+ * "spmm_b_ms", ..., "dist_ms", "dist_flops", "ks_restarts", "ks_ops".  Unknown name ->
+ * ISLE_ERR_ARG.  Reading synchronises the stream. */
+int isle_cuda_get_stat(isle_cuda_ctx *ctx, const char *name, double *value_out);
+int isle_cuda_reset_stats(isle_cuda_ctx *ctx);
+/* Device-side stopwatch: records CUDA events on the context's own stream (the stream every
+ * kernel of the library is launched on).  stop synchronises and returns the elapsed ms. */
+int isle_cuda_timer_start(isle_cuda_ctx *ctx);
+int isle_cuda_timer_stop(isle_cuda_ctx *ctx, double *ms_out);
+/* Select kernel variants for A/B measurements: name in {"dist_kernel"} etc. */
+int isle_cuda_set_option(isle_cuda_ctx *ctx, const char *name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISLE_CUDA_H */

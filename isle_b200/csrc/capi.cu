@@ -1,0 +1,337 @@
+// capi.cu -- extern "C" surface of libisle_cuda.so (include/isle_cuda.h).  Converts C++
+// exceptions into return codes + isle_cuda_last_error(), the convention INTEGRATION.md's
+// replacement translation unit turns back into std::runtime_error for ISLETrain's catch-all
+// (reference drivers/ISLETrain.cpp:48-50).
+#include <cstring>
+
+#include "common.cuh"
+
+using namespace isle;
+
+struct isle_cuda_ctx {
+    Ctx c;
+};
+
+static thread_local std::string g_create_error;
+
+template <class F>
+static int guarded(isle_cuda_ctx *h, F &&f)
+{
+    if (!h) return ISLE_ERR_ARG;
+    try {
+        ISLE_CUDA_CHECK(cudaSetDevice(h->c.device));
+        f(h->c);
+        return ISLE_OK;
+    } catch (const Error &e) {
+        h->c.last_error = e.what();
+        return e.code;
+    } catch (const std::exception &e) {
+        h->c.last_error = e.what();
+        return ISLE_ERR_CUDA;
+    }
+}
+
+static int create_common(isle_cuda_ctx **out, int device, int rank, int world, const void *nccl_id)
+{
+    if (!out) return ISLE_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        g_create_error = "no usable CUDA device (libisle_cuda has no CPU fallback)";
+        return ISLE_ERR_NOGPU;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+        g_create_error = "device is not sm_100 class (libisle_cuda is built for sm_100a only)";
+        return ISLE_ERR_NOGPU;
+    }
+    auto *h = new isle_cuda_ctx();
+    Ctx &c = h->c;
+    c.device = device;
+    c.rank = rank;
+    c.world = world;
+    c.num_sms = prop.multiProcessorCount;
+    try {
+        ISLE_CUDA_CHECK(cudaSetDevice(device));
+        ISLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        ISLE_CUBLAS_CHECK(cublasCreate(&c.cublas));
+        ISLE_CUBLAS_CHECK(cublasSetStream(c.cublas, c.stream));
+        // fp32 FMA GEMMs only: no TF32 / reduced-precision paths in the eigensolver
+        ISLE_CUBLAS_CHECK(cublasSetMathMode(
+            c.cublas, (cublasMath_t)(CUBLAS_DEFAULT_MATH | CUBLAS_MATH_DISALLOW_REDUCED_PRECISION_REDUCTION)));
+        ISLE_CUSOLVER_CHECK(cusolverDnCreate(&c.cusolver));
+        ISLE_CUSOLVER_CHECK(cusolverDnSetStream(c.cusolver, c.stream));
+        if (world > 1) {
+#ifdef ISLE_WITH_NCCL
+            ISLE_REQUIRE(nccl_id != nullptr, ISLE_ERR_ARG, "create_sharded: nccl_id is NULL");
+            ncclUniqueId id;
+            std::memcpy(&id, nccl_id, sizeof(id));
+            ncclResult_t r = ncclCommInitRank(&c.comm, world, id, rank);
+            if (r != ncclSuccess) throw Error(ISLE_ERR_CUDA, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+#else
+            throw Error(ISLE_ERR_ARG, "library built without NCCL");
+#endif
+        }
+    } catch (const std::exception &e) {
+        g_create_error = e.what();
+        delete h;
+        return ISLE_ERR_CUDA;
+    }
+    *out = h;
+    return ISLE_OK;
+}
+
+extern "C" {
+
+int isle_cuda_create(isle_cuda_ctx **ctx, int device) { return create_common(ctx, device, 0, 1, nullptr); }
+
+int isle_cuda_create_sharded(isle_cuda_ctx **ctx, int device, int rank, int world, const void *nccl_id)
+{
+    if (world < 1 || rank < 0 || rank >= world) return ISLE_ERR_ARG;
+    return create_common(ctx, device, rank, world, nccl_id);
+}
+
+int isle_cuda_nccl_unique_id(void *id128)
+{
+#ifdef ISLE_WITH_NCCL
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (!id128 || ncclGetUniqueId(&id) != ncclSuccess) return ISLE_ERR_CUDA;
+    std::memcpy(id128, &id, sizeof(id));
+    return ISLE_OK;
+#else
+    (void)id128;
+    return ISLE_ERR_ARG;
+#endif
+}
+
+void isle_cuda_destroy(isle_cuda_ctx *h)
+{
+    if (!h) return;
+    Ctx &c = h->c;
+    cudaSetDevice(c.device);
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    for (auto &kv : c.stats)
+        for (auto &ev : kv.second.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+#ifdef ISLE_WITH_NCCL
+    if (c.comm) ncclCommDestroy(c.comm);
+#endif
+    if (c.timer0) { cudaEventDestroy(c.timer0); cudaEventDestroy(c.timer1); }
+    if (c.cusolver) cusolverDnDestroy(c.cusolver);
+    if (c.cublas) cublasDestroy(c.cublas);
+    // device buffers are released by the DevBuf destructors inside Ctx
+    cudaStream_t s = c.stream;
+    delete h;
+    if (s) cudaStreamDestroy(s);
+}
+
+const char *isle_cuda_last_error(const isle_cuda_ctx *h) { return h ? h->c.last_error.c_str() : g_create_error.c_str(); }
+
+int isle_cuda_upload_A(isle_cuda_ctx *h, uint64_t V, uint64_t D, int64_t nnz, const float *vals, const uint64_t *rows,
+                       const int64_t *offsets, float avg, uint64_t nz_docs)
+{
+    return guarded(h, [&](Ctx &c) { upload_A(c, V, D, nnz, vals, rows, true, offsets, avg, nz_docs); });
+}
+
+int isle_cuda_upload_A_u32(isle_cuda_ctx *h, uint64_t V, uint64_t D, int64_t nnz, const float *vals,
+                           const uint32_t *rows, const int64_t *offsets, float avg, uint64_t nz_docs)
+{
+    return guarded(h, [&](Ctx &c) { upload_A(c, V, D, nnz, vals, rows, false, offsets, avg, nz_docs); });
+}
+
+int isle_cuda_thresholds(isle_cuda_ctx *h, uint64_t k, float *zetas_out, int64_t *new_nnz_out)
+{
+    return guarded(h, [&](Ctx &c) { compute_thresholds(c, k, zetas_out, new_nnz_out); });
+}
+
+int isle_cuda_build_B(isle_cuda_ctx *h, const uint8_t *select, int64_t *nnzB, uint64_t *DB)
+{
+    return guarded(h, [&](Ctx &c) { build_B(c, select, nnzB, DB); });
+}
+
+int isle_cuda_sampling_weights(isle_cuda_ctx *h, float *out)
+{
+    return guarded(h, [&](Ctx &c) { sampling_weights(c, out); });
+}
+
+int isle_cuda_download_B(isle_cuda_ctx *h, float *vals, uint64_t *rows, int64_t *offsets, uint64_t *orig)
+{
+    return guarded(h, [&](Ctx &c) { download_B(c, vals, rows, offsets, orig); });
+}
+
+int isle_cuda_frobenius(isle_cuda_ctx *h, float *out)
+{
+    return guarded(h, [&](Ctx &c) { *out = frobenius(c); });
+}
+
+int isle_cuda_spsptr_multiply(isle_cuda_ctx *h, int b, const float *X, float *Z)
+{
+    return guarded(h, [&](Ctx &c) {
+        ISLE_REQUIRE(c.have_B, ISLE_ERR_ARG, "spsptr_multiply: build_B first");
+        ISLE_REQUIRE(b >= 1 && b <= 16, ISLE_ERR_ARG, "spsptr_multiply: block size must be in [1,16]");
+        DevBuf<float> dX((size_t)c.V * b), dZ((size_t)c.V * b);
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(dX.p, X, dX.bytes(), cudaMemcpyHostToDevice, c.stream));
+        spsptr_multiply_dev(c, b, dX.p, dZ.p);
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(Z, dZ.p, dZ.bytes(), cudaMemcpyDeviceToHost, c.stream));
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    });
+}
+
+int isle_cuda_block_ks(isle_cuda_ctx *h, uint64_t k, int b, int max_restarts, float tol, uint64_t seed,
+                       float *evalues_out, float *U_out, int *nconv_out)
+{
+    return guarded(h, [&](Ctx &c) { block_ks(c, k, b, max_restarts, tol, seed, evalues_out, U_out, nconv_out); });
+}
+
+int isle_cuda_set_U(isle_cuda_ctx *h, uint64_t k, const float *U)
+{
+    return guarded(h, [&](Ctx &c) {
+        ISLE_REQUIRE(c.have_B && k >= 1 && U, ISLE_ERR_ARG, "set_U: build_B first");
+        c.k = k;
+        c.U.alloc((size_t)c.V * k);
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(c.U.p, U, c.U.bytes(), cudaMemcpyHostToDevice, c.stream));
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        c.have_U = true;
+        c.have_P = false;
+    });
+}
+
+int isle_cuda_project(isle_cuda_ctx *h, float *P_out, float *l2_out)
+{
+    return guarded(h, [&](Ctx &c) {
+        project(c);
+        if (P_out && c.DB)
+            ISLE_CUDA_CHECK(cudaMemcpy2DAsync(P_out, (size_t)c.k * 4, c.P.p, (size_t)c.kp * 4, (size_t)c.k * 4,
+                                              (size_t)c.DB, cudaMemcpyDeviceToHost, c.stream));
+        if (l2_out && c.DB)
+            ISLE_CUDA_CHECK(cudaMemcpyAsync(l2_out, c.p_l2.p, (size_t)c.DB * 4, cudaMemcpyDeviceToHost, c.stream));
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    });
+}
+
+int isle_cuda_kmeanspp(isle_cuda_ctx *h, uint64_t k, uint64_t seed, uint64_t *seeds_out, float *centers_out,
+                       float *residual_out)
+{
+    return guarded(h, [&](Ctx &c) { kmeanspp(c, k, seed, seeds_out, centers_out, residual_out); });
+}
+
+int isle_cuda_lloyd_projected(isle_cuda_ctx *h, uint64_t k, float *centers_inout, int max_reps, uint32_t *assign_out,
+                              double *objective_out, int *iters_out)
+{
+    return guarded(h, [&](Ctx &c) {
+        ISLE_REQUIRE(centers_inout != nullptr && max_reps >= 1, ISLE_ERR_ARG, "lloyd_projected: bad arguments");
+        lloyd_projected(c, k, centers_inout, max_reps, assign_out, objective_out, iters_out);
+    });
+}
+
+int isle_cuda_assign_projected(isle_cuda_ctx *h, uint64_t k, const float *centers, uint32_t *assign_out)
+{
+    return guarded(h, [&](Ctx &c) {
+        ISLE_REQUIRE(centers && assign_out, ISLE_ERR_ARG, "assign_projected: bad arguments");
+        assign_projected(c, k, centers, assign_out);
+    });
+}
+
+int isle_cuda_lift_centers(isle_cuda_ctx *h, uint64_t ncols, const float *in, uint64_t ld_in, float *out)
+{
+    return guarded(h, [&](Ctx &c) { lift_centers(c, ncols, in, ld_in, out); });
+}
+
+int isle_cuda_cleanup_eigensolver(isle_cuda_ctx *h)
+{
+    return guarded(h, [&](Ctx &c) {
+        c.U.release();
+        c.P.release();
+        c.p_l2.release();
+        c.have_U = c.have_P = false;
+    });
+}
+
+int isle_cuda_set_profiling(isle_cuda_ctx *h, int enabled)
+{
+    return guarded(h, [&](Ctx &c) { c.profiling = enabled != 0; });
+}
+
+static void drain(Ctx &c)
+{
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    for (auto &kv : c.stats) {
+        for (auto &ev : kv.second.pending) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) kv.second.ms += ms;
+            cudaEventDestroy(ev.first);
+            cudaEventDestroy(ev.second);
+        }
+        kv.second.pending.clear();
+    }
+}
+
+int isle_cuda_get_stat(isle_cuda_ctx *h, const char *name, double *out)
+{
+    return guarded(h, [&](Ctx &c) {
+        ISLE_REQUIRE(name && out, ISLE_ERR_ARG, "get_stat: bad arguments");
+        drain(c);
+        const std::string n(name);
+        if (n == "launches") { *out = c.launches; return; }
+        if (n == "nnz_B") { *out = (double)c.nnzB; return; }
+        if (n == "D_B") { *out = (double)c.DB; return; }
+        auto ci = c.counters.find(n);
+        if (ci != c.counters.end()) { *out = ci->second; return; }
+        const size_t us = n.rfind('_');
+        if (us != std::string::npos) {
+            const std::string base = n.substr(0, us), field = n.substr(us + 1);
+            auto it = c.stats.find(base);
+            if (field == "ms" || field == "calls" || field == "bytes" || field == "flops") {
+                if (it == c.stats.end()) { *out = 0.0; return; }
+                *out = field == "ms" ? it->second.ms : field == "calls" ? it->second.calls
+                     : field == "bytes" ? it->second.bytes : it->second.flops;
+                return;
+            }
+        }
+        throw Error(ISLE_ERR_ARG, "get_stat: unknown counter " + n);
+    });
+}
+
+int isle_cuda_reset_stats(isle_cuda_ctx *h)
+{
+    return guarded(h, [&](Ctx &c) {
+        drain(c);
+        c.stats.clear();
+        c.counters.clear();
+        c.launches = 0.0;
+    });
+}
+
+int isle_cuda_timer_start(isle_cuda_ctx *h)
+{
+    return guarded(h, [&](Ctx &c) {
+        if (!c.timer0) {
+            ISLE_CUDA_CHECK(cudaEventCreate(&c.timer0));
+            ISLE_CUDA_CHECK(cudaEventCreate(&c.timer1));
+        }
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        ISLE_CUDA_CHECK(cudaEventRecord(c.timer0, c.stream));
+    });
+}
+
+int isle_cuda_timer_stop(isle_cuda_ctx *h, double *ms_out)
+{
+    return guarded(h, [&](Ctx &c) {
+        ISLE_REQUIRE(c.timer0 && ms_out, ISLE_ERR_ARG, "timer_stop: timer_start first");
+        ISLE_CUDA_CHECK(cudaEventRecord(c.timer1, c.stream));
+        ISLE_CUDA_CHECK(cudaEventSynchronize(c.timer1));
+        float ms = 0.f;
+        ISLE_CUDA_CHECK(cudaEventElapsedTime(&ms, c.timer0, c.timer1));
+        *ms_out = ms;
+    });
+}
+
+int isle_cuda_set_option(isle_cuda_ctx *h, const char *name, int value)
+{
+    return guarded(h, [&](Ctx &c) {
+        ISLE_REQUIRE(name, ISLE_ERR_ARG, "set_option: bad arguments");
+        c.options[name] = value;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+// common.cuh -- internal declarations shared by the kernel families of libisle_cuda.
+#pragma once
+
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/isle_cuda.h"
+
+#ifdef ISLE_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace isle {
+
+struct Error : public std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define ISLE_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            throw ::isle::Error(ISLE_ERR_CUDA, std::string(#expr) + ": " +                     \
+                                                   cudaGetErrorString(_e) + " @" + __FILE__ +  \
+                                                   ":" + std::to_string(__LINE__));            \
+    } while (0)
+
+#define ISLE_CUBLAS_CHECK(expr)                                                                \
+    do {                                                                                       \
+        cublasStatus_t _s = (expr);                                                            \
+        if (_s != CUBLAS_STATUS_SUCCESS)                                                       \
+            throw ::isle::Error(ISLE_ERR_CUDA, std::string(#expr) + ": cublas status " +       \
+                                                   std::to_string((int)_s) + " @" + __FILE__ + \
+                                                   ":" + std::to_string(__LINE__));            \
+    } while (0)
+
+#define ISLE_CUSOLVER_CHECK(expr)                                                              \
+    do {                                                                                       \
+        cusolverStatus_t _s = (expr);                                                          \
+        if (_s != CUSOLVER_STATUS_SUCCESS)                                                     \
+            throw ::isle::Error(ISLE_ERR_CUDA, std::string(#expr) + ": cusolver status " +     \
+                                                   std::to_string((int)_s) + " @" + __FILE__ + \
+                                                   ":" + std::to_string(__LINE__));            \
+    } while (0)
+
+#define ISLE_REQUIRE(cond, code, msg)                                  \
+    do {                                                               \
+        if (!(cond)) throw ::isle::Error((code), std::string(msg));    \
+    } while (0)
+
+// Owning device buffer (cudaMalloc / cudaFree); movable, not copyable.
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t n_) { alloc(n_); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t n_) {
+        release();
+        n = n_;
+        if (n) ISLE_CUDA_CHECK(cudaMalloc((void **)&p, n * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// CUDA-event timing of one kernel family on the context stream.
+struct KernelStat {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    double ms = 0.0;
+    double calls = 0.0;
+    double bytes = 0.0;   // algorithmic bytes, summed over calls
+    double flops = 0.0;
+};
+
+struct WorkItem {          // one 4-lane group's share of a sparse pass
+    uint32_t out_row;      // row of the dense output this item accumulates into
+    uint32_t len;          // number of nonzeros
+    int64_t begin;         // first nonzero in the index stream
+};
+
+struct Ctx {
+    int device = 0;
+    int rank = 0, world = 1;
+    cudaStream_t stream = nullptr;
+    cublasHandle_t cublas = nullptr;
+    cusolverDnHandle_t cusolver = nullptr;
+    int num_sms = 148;
+    std::string last_error;
+#ifdef ISLE_WITH_NCCL
+    ncclComm_t comm = nullptr;
+#endif
+
+    // ---- A: normalised doc-major CSC (local slice when sharded)
+    uint64_t V = 0, D = 0, nz_docs = 0;   // nz_docs: GLOBAL count of non-empty docs
+    int64_t nnzA = 0;
+    float avg_doc_sz = 0.f;
+    DevBuf<float> a_val;
+    DevBuf<uint32_t> a_row;
+    DevBuf<int64_t> a_off;
+
+    // ---- thresholds
+    bool have_zeta = false;
+    DevBuf<float> zeta, sqrt_zeta;
+    int64_t new_nnz = 0;                   // local count of kept entries
+
+    // ---- B: pattern-only doc-major CSC + word-major CSR copy (values are sqrt_zeta[row])
+    bool have_B = false;
+    uint64_t DB = 0;
+    int64_t nnzB = 0;
+    DevBuf<uint32_t> b_row;                // [nnzB] word of each nonzero, doc-major
+    DevBuf<int64_t> b_off;                 // [DB+1]
+    DevBuf<uint32_t> b_orig;               // [DB] original (local) doc id
+    bool have_csr = false;
+    DevBuf<uint32_t> csr_col;              // [nnzB] doc of each nonzero, word-major
+    DevBuf<int64_t> csr_off;               // [V+1]
+    DevBuf<WorkItem> items_bt, items_b;    // work lists for Y=B^T X and Z=B Y
+    size_t n_items_bt = 0, n_items_b = 0;
+    DevBuf<float> xs, ybuf, zbuf;          // padded row-major operands of the SpMM pair
+
+    // ---- eigen / projection state
+    uint64_t k = 0;
+    bool have_U = false, have_P = false;
+    DevBuf<float> U;                       // V x k column-major
+    uint64_t kp = 0;                       // padded projection width (multiple of 32)
+    DevBuf<float> P;                       // DB x kp row-major, zero padded
+    DevBuf<float> p_l2;                    // DB
+
+    // ---- stats / options
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    bool profiling = false;
+    double launches = 0.0;
+    std::map<std::string, KernelStat> stats;
+    std::map<std::string, double> counters;
+    std::map<std::string, int> options;
+
+    int opt(const char *name, int dflt) const {
+        auto it = options.find(name);
+        return it == options.end() ? dflt : it->second;
+    }
+};
+
+// RAII: brackets a kernel-family launch with events when profiling is on.
+struct StatScope {
+    Ctx &c;
+    KernelStat *st;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    StatScope(Ctx &ctx, const char *name, double bytes = 0.0, double flops = 0.0) : c(ctx) {
+        st = &c.stats[name];
+        st->calls += 1.0;
+        st->bytes += bytes;
+        st->flops += flops;
+        if (c.profiling) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, c.stream);
+        }
+    }
+    ~StatScope() {
+        if (e0) {
+            cudaEventRecord(e1, c.stream);
+            st->pending.emplace_back(e0, e1);
+        }
+    }
+};
+
+inline void count_launch(Ctx &c, int n = 1) { c.launches += n; }
+
+inline unsigned grid_for(size_t work, unsigned block, unsigned cap = 148u * 16u) {
+    size_t g = (work + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (unsigned)g;
+}
+
+// ---- threshold.cu
+void upload_A(Ctx &c, uint64_t V, uint64_t D, int64_t nnz, const float *vals, const void *rows,
+              bool rows64, const int64_t *offsets, float avg, uint64_t nz_docs);
+void compute_thresholds(Ctx &c, uint64_t k, float *zetas_out, int64_t *new_nnz_out);
+void build_B(Ctx &c, const uint8_t *select, int64_t *nnzB, uint64_t *DB);
+void sampling_weights(Ctx &c, float *out);
+void download_B(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets, uint64_t *orig);
+float frobenius(Ctx &c);
+
+// ---- spmm.cu
+void build_csr(Ctx &c);
+// Z(V x b, column-major, ld=V) = B (B^T X); X column-major ld=V; both on the device.
+void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z);
+
+// ---- blockks.cu
+void block_ks(Ctx &c, uint64_t k, int b, int max_restarts, float tol, uint64_t seed,
+              float *evalues_out, float *U_out, int *nconv_out);
+
+// ---- kmeans.cu
+void project(Ctx &c);
+void kmeanspp(Ctx &c, uint64_t k, uint64_t seed, uint64_t *seeds_out, float *centers_out,
+              float *residual_out);
+void lloyd_projected(Ctx &c, uint64_t k, float *centers_inout, int max_reps,
+                     uint32_t *assign_out, double *objective_out, int *iters_out);
+void assign_projected(Ctx &c, uint64_t k, const float *centers, uint32_t *assign_out);
+void lift_centers(Ctx &c, uint64_t ncols, const float *in, uint64_t ld_in, float *out);
+
+// ---- collectives (no-ops when world == 1)
+void allreduce_sum_f32(Ctx &c, float *buf, size_t n);
+void allreduce_sum_u32(Ctx &c, uint32_t *buf, size_t n);
+void allreduce_sum_u64(Ctx &c, unsigned long long *buf, size_t n);
+void allreduce_sum_f64(Ctx &c, double *buf, size_t n);
+void allreduce_max_u32(Ctx &c, uint32_t *buf, size_t n);
+void allgather_u64(Ctx &c, const unsigned long long *send, unsigned long long *recv);  // 1 per rank
+void bcast_f32(Ctx &c, float *buf, size_t n, int root);
+
+}  // namespace isle

@@ -1,0 +1,516 @@
+// kmeans.cu -- kernel family (3): k-means++ seeding and Lloyd's iterations on the rank-k
+// projection of the documents.
+//
+// The reference never materialises the projection (USE_EXPLICIT_PROJECTED_MATRIX false,
+// include/hyperparams.h:44): per 2^18-doc block it forms -2 U C^T (vocab x k) and multiplies by
+// the sparse block (src/sparseMatrix.cpp:1794-1849).  With 180 GB of HBM the idiomatic form is
+// the reference's own disabled "explicit" one (src/denseMatrix.cpp:504-530): materialise
+// P = B^T U once (docs x k), after which
+//     dist[d,c] = ((-2 P_d . C_c) + ||C_c||^2) + ||P_d||^2          (order of :1820-1846)
+// is a dense docs x centers contraction with a fused epilogue:
+//     assignment  argmin_c |dist[d,c]|, first index on ties (cblas_isamin, :1868-1870)
+//     k-means++   min_dist[d] = min(min_dist[d], max(dist, 0))      (:2112-2126)
+// followed by one pass over P that accumulates center sums and counts (:1959-1992).
+// dist_kernel selects the contraction engine: 0 = SIMT fp32 FMA tile kernel (this file),
+// 1 = tcgen05 split-TF32 kernel (dist_tc.cu).
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <random>
+
+#include "common.cuh"
+
+namespace isle {
+
+void dist_tc_launch(Ctx &c, const float *P, const float *d2, uint32_t DB, uint32_t kp, const float *C,
+                    const float *c2, uint32_t ncent, int mode, uint32_t *assign, float *min_dist);
+bool dist_tc_supported(const Ctx &c, uint32_t kp, uint32_t ncent);
+
+// ------------------------------------------------------------------------------ projection
+// Us[w, j] = sqrt_zeta[w] * U[w + j V], row-major with row stride kp (zero padded).
+__global__ void __launch_bounds__(256)
+transpose_scale_kernel(const float *__restrict__ U, uint32_t V, uint32_t k, uint32_t kp,
+                       const float *__restrict__ scale, float *__restrict__ Us)
+{
+    __shared__ float tile[32][33];
+    const uint32_t w0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (uint32_t r = ty; r < 32; r += 8) {
+        const uint32_t j = j0 + r, w = w0 + tx;
+        tile[r][tx] = (j < k && w < V) ? U[(size_t)j * V + w] : 0.0f;
+    }
+    __syncthreads();
+    for (uint32_t r = ty; r < 32; r += 8) {
+        const uint32_t w = w0 + r, j = j0 + tx;
+        if (w < V && j < kp) Us[(size_t)w * kp + j] = tile[tx][r] * scale[w];
+    }
+}
+
+// One warp per document: P[d,:] = sum_{w in d} Us[w,:]; l2[d] = ||P[d,:]||^2
+// (multiply_with / UT_times_docs + compute_projected_docs_l2sq, src/sparseMatrix.cpp:1749-1791,1888-1918)
+__global__ void __launch_bounds__(256)
+project_kernel(const uint32_t *__restrict__ b_row, const int64_t *__restrict__ b_off, uint32_t DB,
+               const float4 *__restrict__ Us, uint32_t kp4, float4 *__restrict__ P, float *__restrict__ l2)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (; d < DB; d += nw) {
+        const int64_t b = b_off[d], e = b_off[d + 1];
+        float nrm = 0.f;
+        for (uint32_t c0 = 0; c0 < kp4; c0 += 32) {
+            const uint32_t col = c0 + lane;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col < kp4) {
+                int64_t p = b;
+                for (; p + 4 <= e; p += 4) {
+                    const uint32_t w0 = b_row[p], w1 = b_row[p + 1], w2 = b_row[p + 2], w3 = b_row[p + 3];
+                    const float4 v0 = __ldg(Us + (size_t)w0 * kp4 + col);
+                    const float4 v1 = __ldg(Us + (size_t)w1 * kp4 + col);
+                    const float4 v2 = __ldg(Us + (size_t)w2 * kp4 + col);
+                    const float4 v3 = __ldg(Us + (size_t)w3 * kp4 + col);
+                    acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+                    acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+                    acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+                    acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+                }
+                for (; p < e; ++p) {
+                    const float4 v = __ldg(Us + (size_t)b_row[p] * kp4 + col);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                P[(size_t)d * kp4 + col] = acc;
+                nrm += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+        if (lane == 0) l2[d] = nrm;
+    }
+}
+
+void project(Ctx &c)
+{
+    ISLE_REQUIRE(c.have_B && c.have_U, ISLE_ERR_ARG, "project: needs B and U");
+    if (c.have_P) return;
+    const uint32_t V = (uint32_t)c.V, k = (uint32_t)c.k, DB = (uint32_t)c.DB;
+    c.kp = ((uint64_t)k + 31) / 32 * 32;
+    const uint32_t kp = (uint32_t)c.kp;
+    DevBuf<float> Us((size_t)V * kp);
+    c.P.alloc((size_t)std::max<uint32_t>(DB, 1) * kp);
+    c.p_l2.alloc(std::max<uint32_t>(DB, 1));
+    dim3 tg((V + 31) / 32, kp / 32);
+    transpose_scale_kernel<<<tg, 256, 0, c.stream>>>(c.U.p, V, k, kp, c.sqrt_zeta.p, Us.p);
+    count_launch(c);
+    {
+        // SURVEY 8(d) row (2'): flops = 2 nnz k ; compulsory bytes = nnz*8 + D_B k 4 + V k 4
+        StatScope s(c, "project", (double)c.nnzB * 8.0 + ((double)DB + V) * k * 4.0, 2.0 * c.nnzB * k);
+        if (DB) {
+            project_kernel<<<grid_for((size_t)DB * 32, 256, c.num_sms * 8), 256, 0, c.stream>>>(
+                c.b_row.p, c.b_off.p, DB, reinterpret_cast<const float4 *>(Us.p), kp / 4,
+                reinterpret_cast<float4 *>(c.P.p), c.p_l2.p);
+            count_launch(c);
+        }
+    }
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.have_P = true;
+}
+
+// ------------------------------------------------------------------- distance contraction
+// SIMT engine: 64 docs x 64 centers per CTA step, 16-deep K slabs in shared memory, 4x4
+// register tile per thread, fp32 FMA.  MODE 0: abs-argmin (first index).  MODE 1: clamped min.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+dist_simt_kernel(const float *__restrict__ P, const float *__restrict__ d2, uint32_t DB, uint32_t kp,
+                 const float *__restrict__ C, const float *__restrict__ c2, uint32_t ncent,
+                 uint32_t *__restrict__ assign, float *__restrict__ min_dist)
+{
+    constexpr int TM = 64, TN = 64, TK = 16;
+    __shared__ float sA[TK][TM + 4];
+    __shared__ float sB[TK][TN + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const uint32_t row0 = blockIdx.x * TM;
+    float best[4];
+    uint32_t besti[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { best[i] = FLT_MAX; besti[i] = 0; }
+    float rd2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t r = row0 + ty * 4 + i;
+        rd2[i] = r < DB ? d2[r] : 0.f;
+    }
+    for (uint32_t n0 = 0; n0 < ncent; n0 += TN) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (uint32_t k0 = 0; k0 < kp; k0 += TK) {
+            // 64 rows x 16 k: 1024 floats, 4 per thread as one float4 along k
+            {
+                const int r = threadIdx.x >> 2, kq = (threadIdx.x & 3) * 4;
+                const uint32_t gr = row0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gr < DB) v = *reinterpret_cast<const float4 *>(P + (size_t)gr * kp + k0 + kq);
+                sA[kq][r] = v.x; sA[kq + 1][r] = v.y; sA[kq + 2][r] = v.z; sA[kq + 3][r] = v.w;
+                const uint32_t gc = n0 + r;
+                float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gc < ncent) u = *reinterpret_cast<const float4 *>(C + (size_t)gc * kp + k0 + kq);
+                sB[kq][r] = u.x; sB[kq + 1][r] = u.y; sB[kq + 2][r] = u.z; sB[kq + 3][r] = u.w;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < TK; ++kk) {
+                const float4 a = *reinterpret_cast<const float4 *>(&sA[kk][ty * 4]);
+                const float4 bq = *reinterpret_cast<const float4 *>(&sB[kk][tx * 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+        // epilogue for this center tile
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float bl = FLT_MAX;
+            uint32_t bi = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t cidx = n0 + tx * 4 + j;
+                if (cidx < ncent) {
+                    float v = __fadd_rn(__fadd_rn(-2.0f * acc[i][j], __ldg(c2 + cidx)), rd2[i]);
+                    v = MODE == 0 ? fabsf(v) : fmaxf(v, 0.0f);
+                    if (v < bl) { bl = v; bi = cidx; }
+                }
+            }
+            // reduce over the 16 tx lanes of this row (smaller index wins ties)
+#pragma unroll
+            for (int o = 8; o; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bl, o);
+                const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov < bl || (ov == bl && oi < bi)) { bl = ov; bi = oi; }
+            }
+            if (bl < best[i]) { best[i] = bl; besti[i] = bi; }
+        }
+    }
+    if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t r = row0 + ty * 4 + i;
+            if (r < DB) {
+                if (MODE == 0) assign[r] = besti[i];
+                else min_dist[r] = fminf(min_dist[r], best[i]);
+            }
+        }
+    }
+}
+
+__global__ void row_l2_kernel(const float *__restrict__ C, uint32_t rows, uint32_t kp, float *__restrict__ out)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    float s = 0.f;
+    for (uint32_t j = lane; j < kp; j += 32) { const float v = C[(size_t)r * kp + j]; s = fmaf(v, v, s); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[r] = s;
+}
+
+// mode 0: assign[d] = argmin |dist| ; mode 1: min_dist[d] = min(min_dist[d], max(dist,0))
+static void distance_pass(Ctx &c, const float *C, const float *c2, uint32_t ncent, int mode, uint32_t *assign,
+                          float *min_dist)
+{
+    const uint32_t DB = (uint32_t)c.DB, kp = (uint32_t)c.kp;
+    if (!DB) return;
+    const bool tc = c.opt("dist_kernel", 1) == 1 && dist_tc_supported(c, kp, ncent);
+    // logical flops = 2 D_B ncent k
+    StatScope s(c, mode == 0 ? (tc ? "dist_tc" : "dist_simt") : (tc ? "pp_dist_tc" : "pp_dist_simt"),
+                (double)DB * kp * 4.0 + (double)DB * 8.0, 2.0 * (double)DB * ncent * (double)c.k);
+    if (tc) {
+        dist_tc_launch(c, c.P.p, c.p_l2.p, DB, kp, C, c2, ncent, mode, assign, min_dist);
+        return;
+    }
+    const unsigned grid = (DB + 63) / 64;
+    if (mode == 0)
+        dist_simt_kernel<0><<<grid, 256, 0, c.stream>>>(c.P.p, c.p_l2.p, DB, kp, C, c2, ncent, assign, min_dist);
+    else
+        dist_simt_kernel<1><<<grid, 256, 0, c.stream>>>(c.P.p, c.p_l2.p, DB, kp, C, c2, ncent, assign, min_dist);
+    count_launch(c);
+}
+
+// ------------------------------------------------------------------------------ Lloyd step
+// One warp per doc: sums[assign[d], :] += P[d, :], counts[assign[d]] += 1   (:1959-1984)
+__global__ void __launch_bounds__(256)
+accumulate_kernel(const float4 *__restrict__ P, const uint32_t *__restrict__ assign, uint32_t DB, uint32_t kp4,
+                  float4 *__restrict__ sums, uint32_t *__restrict__ counts)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (; d < DB; d += nw) {
+        const uint32_t cidx = assign[d];
+        for (uint32_t col = lane; col < kp4; col += 32)
+            atomicAdd(sums + (size_t)cidx * kp4 + col, P[(size_t)d * kp4 + col]);
+        if (lane == 0) atomicAdd(counts + cidx, 1u);
+    }
+}
+
+// centers = sums * (1/count) for non-empty clusters, zero otherwise (:1988-1992)
+__global__ void finalize_centers_kernel(const float *__restrict__ sums, const uint32_t *__restrict__ counts,
+                                        uint32_t k, uint32_t kp, float *__restrict__ C)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)k * kp) return;
+    const uint32_t cnt = counts[i / kp];
+    const float div = (float)cnt;
+    C[i] = cnt ? sums[i] * (1.0f / div) : 0.0f;
+}
+
+__global__ void count_diff_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, uint32_t n,
+                                  uint32_t *__restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t diff = 0;
+    for (; i < n; i += stride) diff += (a[i] != b[i]);
+    typedef cub::BlockReduce<uint32_t, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const uint32_t t = BR(tmp).Sum(diff);
+    if (threadIdx.x == 0 && t) atomicAdd(out, t);
+}
+
+__global__ void __launch_bounds__(256)
+objective_kernel(const float *__restrict__ P, const float *__restrict__ C, const uint32_t *__restrict__ assign,
+                 uint32_t DB, uint32_t kp, double *__restrict__ out)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    double s = 0.0;
+    for (; d < DB; d += nw) {
+        const float *p = P + (size_t)d * kp, *cc = C + (size_t)assign[d] * kp;
+        for (uint32_t j = lane; j < kp; j += 32) { const double t = (double)p[j] - (double)cc[j]; s += t * t; }
+    }
+    typedef cub::BlockReduce<double, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const double t = BR(tmp).Sum(s);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+}
+
+struct CentersDev {
+    DevBuf<float> C, c2;
+    uint32_t k, kp;
+    CentersDev(Ctx &c, uint32_t k_, uint32_t kp_, const float *host) : C((size_t)k_ * kp_), c2(k_), k(k_), kp(kp_)
+    {
+        ISLE_CUDA_CHECK(cudaMemsetAsync(C.p, 0, C.bytes(), c.stream));
+        if (host)
+            ISLE_CUDA_CHECK(cudaMemcpy2DAsync(C.p, (size_t)kp * 4, host, (size_t)k * 4, (size_t)k * 4, k,
+                                              cudaMemcpyHostToDevice, c.stream));
+    }
+    void norms(Ctx &c)
+    {
+        row_l2_kernel<<<(k * 32 + 255) / 256, 256, 0, c.stream>>>(C.p, k, kp, c2.p);
+        count_launch(c);
+    }
+};
+
+static void require_k(Ctx &c, uint64_t k)
+{
+    ISLE_REQUIRE(c.have_U && c.have_B, ISLE_ERR_ARG, "k-means: needs B and U (run block_ks or set_U)");
+    // the reference's projected k-means only supports #centers == k
+    ISLE_REQUIRE(k == c.k, ISLE_ERR_ARG, "k-means: number of centers must equal the eigensolver's k");
+    project(c);
+}
+
+void assign_projected(Ctx &c, uint64_t k, const float *centers, uint32_t *assign_out)
+{
+    require_k(c, k);
+    CentersDev cd(c, (uint32_t)k, (uint32_t)c.kp, centers);
+    cd.norms(c);
+    DevBuf<uint32_t> a(std::max<uint64_t>(c.DB, 1));
+    distance_pass(c, cd.C.p, cd.c2.p, (uint32_t)k, 0, a.p, nullptr);
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(assign_out, a.p, (size_t)c.DB * 4, cudaMemcpyDeviceToHost, c.stream));
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+void lloyd_projected(Ctx &c, uint64_t k64, float *centers_inout, int max_reps, uint32_t *assign_out,
+                     double *objective_out, int *iters_out)
+{
+    require_k(c, k64);
+    const uint32_t k = (uint32_t)k64, kp = (uint32_t)c.kp, DB = (uint32_t)c.DB;
+    CentersDev cd(c, k, kp, centers_inout);
+    DevBuf<uint32_t> a0(std::max<uint32_t>(DB, 1)), a1(std::max<uint32_t>(DB, 1)), counts(k), ndiff(1);
+    DevBuf<float> sums((size_t)k * kp);
+    uint32_t *cur = a0.p, *prev = a1.p;
+    int iters = 0;
+    for (int it = 0; it < max_reps; ++it) {
+        StatScope s(c, "lloyd_iter");
+        cd.norms(c);
+        distance_pass(c, cd.C.p, cd.c2.p, k, 0, cur, nullptr);
+        ISLE_CUDA_CHECK(cudaMemsetAsync(sums.p, 0, sums.bytes(), c.stream));
+        ISLE_CUDA_CHECK(cudaMemsetAsync(counts.p, 0, counts.bytes(), c.stream));
+        {
+            StatScope s2(c, "lloyd_accum", (double)DB * kp * 4.0 + (double)DB * 4.0);
+            if (DB) {
+                accumulate_kernel<<<grid_for((size_t)DB * 32, 256, c.num_sms * 8), 256, 0, c.stream>>>(
+                    reinterpret_cast<const float4 *>(c.P.p), cur, DB, kp / 4, reinterpret_cast<float4 *>(sums.p), counts.p);
+                count_launch(c);
+            }
+        }
+        if (c.world > 1) {
+            allreduce_sum_f32(c, sums.p, sums.n);
+            allreduce_sum_u32(c, counts.p, counts.n);
+        }
+        finalize_centers_kernel<<<(unsigned)(((size_t)k * kp + 255) / 256), 256, 0, c.stream>>>(sums.p, counts.p, k, kp, cd.C.p);
+        count_launch(c);
+        ++iters;
+        // converged when the partition equals the previous one (:2044-2064)
+        uint32_t nd = 1;
+        if (it > 0) {
+            ISLE_CUDA_CHECK(cudaMemsetAsync(ndiff.p, 0, 4, c.stream));
+            if (DB) {
+                count_diff_kernel<<<grid_for(DB, 256, c.num_sms * 4), 256, 0, c.stream>>>(cur, prev, DB, ndiff.p);
+                count_launch(c);
+            }
+            if (c.world > 1) allreduce_sum_u32(c, ndiff.p, 1);
+            ISLE_CUDA_CHECK(cudaMemcpyAsync(&nd, ndiff.p, 4, cudaMemcpyDeviceToHost, c.stream));
+            ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        }
+        std::swap(cur, prev);   // prev now holds this iteration's partition
+        if (nd == 0) break;
+    }
+    const uint32_t *final_assign = prev;
+    if (objective_out) {
+        DevBuf<double> obj(1);
+        ISLE_CUDA_CHECK(cudaMemsetAsync(obj.p, 0, 8, c.stream));
+        if (DB) {
+            objective_kernel<<<grid_for((size_t)DB * 32, 256, c.num_sms * 8), 256, 0, c.stream>>>(c.P.p, cd.C.p, final_assign, DB, kp, obj.p);
+            count_launch(c);
+        }
+        if (c.world > 1) allreduce_sum_f64(c, obj.p, 1);
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(objective_out, obj.p, 8, cudaMemcpyDeviceToHost, c.stream));
+    }
+    if (assign_out)
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(assign_out, final_assign, (size_t)DB * 4, cudaMemcpyDeviceToHost, c.stream));
+    ISLE_CUDA_CHECK(cudaMemcpy2DAsync(centers_inout, (size_t)k * 4, cd.C.p, (size_t)kp * 4, (size_t)k * 4, k,
+                                      cudaMemcpyDeviceToHost, c.stream));
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    if (iters_out) *iters_out = iters;
+}
+
+// ------------------------------------------------------------------------------- k-means++
+struct F2D {
+    __host__ __device__ double operator()(float x) const { return (double)x; }
+};
+
+// first index i with cumul[i] > t  ==  upper_bound(dist_cumul, t) - 1 of the reference (:2187)
+__global__ void upper_bound_kernel(const double *__restrict__ cumul, uint32_t n, const double *__restrict__ t,
+                                   int nt, uint32_t *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    uint32_t lo = 0, hi = n;
+    const double tv = t[i];
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (cumul[mid] > tv) hi = mid; else lo = mid + 1;
+    }
+    out[i] = lo < n ? lo : n - 1;
+}
+
+__global__ void fill_kernel(float *__restrict__ p, size_t n, float v)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+void kmeanspp(Ctx &c, uint64_t k64, uint64_t seed, uint64_t *seeds_out, float *centers_out, float *residual_out)
+{
+    require_k(c, k64);
+    ISLE_REQUIRE(c.world == 1, ISLE_ERR_ARG, "kmeanspp: sharded seeding goes through kmeanspp_sharded");
+    const uint32_t k = (uint32_t)k64, kp = (uint32_t)c.kp, DB = (uint32_t)c.DB;
+    ISLE_REQUIRE(DB >= k, ISLE_ERR_ARG, "kmeanspp: fewer documents than centers");   // :2137
+    std::mt19937_64 rng(seed);
+    std::uniform_real_distribution<double> uni(0.0, 1.0);
+    DevBuf<float> min_dist(DB), cc((size_t)k * kp), c2(k);
+    DevBuf<double> cumul(DB), dt(64);
+    DevBuf<uint32_t> cand(64);
+    fill_kernel<<<grid_for(DB, 256), 256, 0, c.stream>>>(min_dist.p, DB, FLT_MAX);   // :2149
+    count_launch(c);
+    size_t tb = 0;
+    auto it = cub::TransformInputIterator<double, F2D, float *>(min_dist.p, F2D());
+    cub::DeviceScan::InclusiveSum(nullptr, tb, it, cumul.p, (int)DB, c.stream);
+    DevBuf<uint8_t> tmp(tb);
+
+    std::vector<uint32_t> centers;
+    auto add_center = [&](uint32_t doc) {
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(cc.p + (size_t)centers.size() * kp, c.P.p + (size_t)doc * kp, (size_t)kp * 4,
+                                        cudaMemcpyDeviceToDevice, c.stream));
+        centers.push_back(doc);
+    };
+    add_center((uint32_t)(rng() % DB));   // :2150 picks an arbitrary first doc
+    int new_added = 1;
+    double total = 0.0;
+    while (centers.size() < k) {
+        StatScope s(c, "pp_round");
+        const uint32_t first = (uint32_t)centers.size() - new_added;
+        row_l2_kernel<<<(new_added * 32 + 255) / 256, 256, 0, c.stream>>>(cc.p + (size_t)first * kp, new_added, kp, c2.p + first);
+        count_launch(c);
+        distance_pass(c, cc.p + (size_t)first * kp, c2.p + first, (uint32_t)new_added, 1, nullptr, min_dist.p);
+        ISLE_CUDA_CHECK(cub::DeviceScan::InclusiveSum(tmp.p, tb, it, cumul.p, (int)DB, c.stream));
+        count_launch(c);
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(&total, cumul.p + (DB - 1), 8, cudaMemcpyDeviceToHost, c.stream));
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        // draw 1 + sqrt(max(s-5,0)) candidates (:2181-2199); duplicates are skipped
+        const int s_now = (int)centers.size();
+        int ndraw = 0;
+        std::vector<double> ts;
+        for (int d = 0; d < 1 + std::sqrt((double)(s_now - 5 > 0 ? s_now - 5 : 0)); ++d) { ts.push_back(total * uni(rng)); ++ndraw; }
+        ndraw = std::min(ndraw, 64);
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(dt.p, ts.data(), (size_t)ndraw * 8, cudaMemcpyHostToDevice, c.stream));
+        upper_bound_kernel<<<1, 64, 0, c.stream>>>(cumul.p, DB, dt.p, ndraw, cand.p);
+        count_launch(c);
+        std::vector<uint32_t> hc(ndraw);
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(hc.data(), cand.p, (size_t)ndraw * 4, cudaMemcpyDeviceToHost, c.stream));
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        new_added = 0;
+        for (int d = 0; d < ndraw && centers.size() < k; ++d) {
+            if (std::find(centers.begin(), centers.end(), hc[d]) == centers.end()) { add_center(hc[d]); ++new_added; }
+        }
+        if (new_added == 0 && total <= 0.0) {
+            // degenerate corpus (all remaining docs coincide with a center): fall back to unused docs
+            for (uint32_t d = 0; d < DB && centers.size() < k; ++d)
+                if (std::find(centers.begin(), centers.end(), d) == centers.end()) { add_center(d); ++new_added; }
+        }
+    }
+    if (seeds_out) for (uint32_t i = 0; i < k; ++i) seeds_out[i] = centers[i];
+    if (centers_out)   // kmeans_init_on_projected_space copies U^T doc for each seed (:2232-2234)
+        ISLE_CUDA_CHECK(cudaMemcpy2DAsync(centers_out, (size_t)k * 4, cc.p, (size_t)kp * 4, (size_t)k * 4, k,
+                                          cudaMemcpyDeviceToHost, c.stream));
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    if (residual_out) *residual_out = (float)total;
+}
+
+// --------------------------------------------------------------------------------- lift
+void lift_centers(Ctx &c, uint64_t ncols, const float *in, uint64_t ld_in, float *out)
+{
+    ISLE_REQUIRE(c.have_U, ISLE_ERR_ARG, "lift_centers: needs U");
+    ISLE_REQUIRE(ld_in >= c.k, ISLE_ERR_ARG, "lift_centers: ld_in < k");   // :1445
+    const int V = (int)c.V, k = (int)c.k, nc = (int)ncols;
+    DevBuf<float> din((size_t)ld_in * ncols), dout((size_t)V * ncols);
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(din.p, in, din.bytes(), cudaMemcpyHostToDevice, c.stream));
+    const float one = 1.f, zero = 0.f;
+    ISLE_CUBLAS_CHECK(cublasSgemm(c.cublas, CUBLAS_OP_N, CUBLAS_OP_N, V, nc, k, &one, c.U.p, V, din.p, (int)ld_in, &zero,
+                                  dout.p, V));
+    count_launch(c);
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(out, dout.p, dout.bytes(), cudaMemcpyDeviceToHost, c.stream));
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+}  // namespace isle

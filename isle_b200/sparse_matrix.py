@@ -1,0 +1,251 @@
+"""Host-side mirror of the reference's matrix interface for the spectral core.
+
+Same method names, argument meaning and error behaviour as ``ISLE::SparseMatrix<float>`` /
+``ISLE::FPSparseMatrix<float>`` (reference include/sparseMatrix.h), each method forwarding to
+the C ABI of libisle_cuda.so exactly as the C++ replacement TU does
+(isle_b200/shim/sparseMatrix_cuda.cpp).  The parity tests therefore read
+like ``ISLETrainer::train()`` (reference src/trainer.cpp:430-554):
+
+    A = SparseMatrix(V, D); A.populate_normalized(vals, rows, offsets, avg_doc_sz, nz_docs)
+    freqs = A.list_word_freqs_by_sorting()
+    zetas, new_nnzs = A.compute_thresholds(0, V, freqs, k)
+    B = FPSparseMatrix(A); original_cols = B.threshold_and_copy(A, zetas, new_nnzs)
+    B.initialize_for_eigensolver(k); evalues = B.compute_block_ks(k)
+    seeds, centers_lowd, res = B.kmeans_init_on_projected_space(k, 1)
+    B.run_lloyds_on_projected_space(k, centers_lowd, None, 10)
+    centers = B.left_multiply_by_U_Spectra(centers_lowd, k, k)
+    B.cleanup_after_eigensolver()
+
+Host arrays are numpy; index widths are the reference's (u64 rows, i64 offsets).  Everything
+numeric happens on the GPU inside the library; there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _capi
+from ._capi import Context, IsleCudaError, ptr
+
+# reference include/hyperparams.h
+BLOCK_KS_BLOCK_SIZE = 10
+BLOCK_KS_MAX_ITERS = 100
+BLOCK_KS_TOLERANCE = 1e-4
+KMEANS_INIT_REPS = 1
+MAX_KMEANS_LOWD_REPS = 10
+
+
+class SparseMatrix:
+    """``ISLE::SparseMatrix<float>``: the normalised doc-major CSC of A on the device."""
+
+    def __init__(self, vocab_size: int, num_docs: int, ctx: Optional[Context] = None, device: int = 0):
+        self._vocab_size, self._num_docs = int(vocab_size), int(num_docs)
+        self.ctx = ctx if ctx is not None else Context(device)
+        self._nnzs = 0
+        self.avg_doc_sz = 0.0
+        self._nz_docs = 0
+
+    def vocab_size(self) -> int:
+        return self._vocab_size
+
+    def num_docs(self) -> int:
+        return self._num_docs
+
+    def get_nnzs(self) -> int:
+        return self._nnzs
+
+    def populate_normalized(self, normalized_vals, rows, offsets, avg_doc_sz: float, nz_docs: int) -> None:
+        """State after populate_CSC + normalize_docs (src/sparseMatrix.cpp:58-167): hands the
+        normalised CSC to the device (isle_cuda_upload_A)."""
+        vals = np.ascontiguousarray(normalized_vals, dtype=np.float32)
+        offs = np.ascontiguousarray(offsets, dtype=np.int64)
+        assert offs.shape[0] == self._num_docs + 1
+        self._nnzs = int(offs[-1])
+        self.avg_doc_sz, self._nz_docs = float(avg_doc_sz), int(nz_docs)
+        rows = np.ascontiguousarray(rows)
+        fn = "isle_cuda_upload_A" if rows.dtype == np.uint64 else "isle_cuda_upload_A_u32"
+        if rows.dtype not in (np.uint64, np.uint32):
+            rows = rows.astype(np.uint32)
+        self.ctx.call(fn, self._vocab_size, self._num_docs, self._nnzs, ptr(vals), ptr(rows), ptr(offs),
+                      C.c_float(self.avg_doc_sz), self._nz_docs)
+
+    def list_word_freqs_by_sorting(self):
+        """src/sparseMatrix.cpp:289-333.  ``freqs`` is only a hand-off to compute_thresholds;
+        the device path needs no word-major lists, so this is a no-op returning a token."""
+        return None
+
+    def compute_thresholds(self, word_begin: int, word_end: int, freqs, num_topics: int) -> Tuple[np.ndarray, int]:
+        """src/sparseMatrix.cpp:357-485.  Returns (zetas float32[V], #entries >= threshold)."""
+        if word_begin != 0 or word_end != self._vocab_size:
+            raise ValueError("device path computes thresholds for the whole vocabulary at once")
+        zetas = np.zeros(self._vocab_size, dtype=np.float32)
+        nn = C.c_int64()
+        self.ctx.call("isle_cuda_thresholds", int(num_topics), ptr(zetas), C.byref(nn))
+        return zetas, int(nn.value)
+
+
+class FPSparseMatrix:
+    """``ISLE::FPSparseMatrix<float>``: the thresholded matrix B and everything train() does
+    with it between trainer.cpp:475 and :554."""
+
+    def __init__(self, A: SparseMatrix):
+        self.ctx = A.ctx
+        self._vocab_size = A.vocab_size()
+        self._num_docs = A.num_docs()
+        self._nnzs = 0
+        self.U_cols = 0
+
+    def vocab_size(self) -> int:
+        return self._vocab_size
+
+    def num_docs(self) -> int:
+        return self._num_docs
+
+    def get_nnzs(self) -> int:
+        return self._nnzs
+
+    # -- stage B
+    def threshold_and_copy(self, A: SparseMatrix, zetas, nnzs: int) -> np.ndarray:
+        """src/sparseMatrix.cpp:1285-1361.  Returns original_cols (uint64[D_B])."""
+        return self._build(None)
+
+    def sampled_threshold_and_copy(self, A: SparseMatrix, zetas, nnzs: int, sample_rate: float,
+                                   rng: Optional[np.random.Generator] = None,
+                                   select_docs: Optional[np.ndarray] = None) -> np.ndarray:
+        """src/sparseMatrix.cpp:1365-1435.  weight_d = sum zeta over kept entries (device);
+        key_d = u^(1/weight_d); keep the floor(rate*D) largest keys (A-Res sampling).  The
+        reference draws u from libc rand() inside a parallel loop (racy); here the
+        caller supplies the generator, or the selection mask itself for parity runs."""
+        if select_docs is None:
+            w = np.zeros(A.num_docs(), dtype=np.float32)
+            self.ctx.call("isle_cuda_sampling_weights", ptr(w))
+            rng = rng or np.random.default_rng(0)
+            u = rng.random(A.num_docs())
+            dice = np.where(w == 0, 0.0, np.power(u, 1.0 / np.maximum(w, 1e-30))).astype(np.float32)
+            nth = int(np.float32(sample_rate) * np.float32(A.num_docs()))
+            pivot = np.partition(dice, len(dice) - 1 - nth)[len(dice) - 1 - nth] if nth < len(dice) else 0.0
+            select_docs = dice >= pivot
+        return self._build(np.ascontiguousarray(select_docs, dtype=np.uint8))
+
+    def _build(self, mask) -> np.ndarray:
+        nnzB, DB = C.c_int64(), C.c_uint64()
+        self.ctx.call("isle_cuda_build_B", ptr(mask), C.byref(nnzB), C.byref(DB))
+        self._nnzs, self._num_docs = int(nnzB.value), int(DB.value)
+        oc = np.zeros(self._num_docs, dtype=np.uint64)
+        self.ctx.call("isle_cuda_download_B", None, None, None, ptr(oc))
+        return oc
+
+    def download(self):
+        """CSC arrays in the reference's layout (vals f32, rows u64, offsets i64)."""
+        vals = np.zeros(self._nnzs, dtype=np.float32)
+        rows = np.zeros(self._nnzs, dtype=np.uint64)
+        offs = np.zeros(self._num_docs + 1, dtype=np.int64)
+        oc = np.zeros(self._num_docs, dtype=np.uint64)
+        self.ctx.call("isle_cuda_download_B", ptr(vals), ptr(rows), ptr(offs), ptr(oc))
+        return vals, rows, offs, oc
+
+    def frobenius(self) -> float:
+        """src/sparseMatrix.cpp:1096-1100."""
+        v = C.c_float()
+        self.ctx.call("isle_cuda_frobenius", C.byref(v))
+        return float(v.value)
+
+    # -- stage C
+    def initialize_for_eigensolver(self, num_topics: int) -> None:
+        """src/sparseMatrix.cpp:1150-1158 (U is allocated by the library)."""
+        self.U_cols = int(num_topics)
+
+    def multiply(self, X: np.ndarray) -> np.ndarray:
+        """MKL_SpSpTrProd::multiply (include/matUtils.h:336-365): B (B^T X), X is V x b."""
+        X = np.asarray(X, dtype=np.float32)
+        b = X.shape[1]
+        Xc = np.ascontiguousarray(X.T)          # column-major V x b == C-order b x V
+        Zc = np.zeros_like(Xc)
+        self.ctx.call("isle_cuda_spsptr_multiply", int(b), ptr(Xc), ptr(Zc))
+        return Zc.T.copy()
+
+    def compute_block_ks(self, num_topics: int, *, block_size: int = BLOCK_KS_BLOCK_SIZE,
+                         max_iters: int = BLOCK_KS_MAX_ITERS, tol: float = BLOCK_KS_TOLERANCE,
+                         seed: int = 0, want_U: bool = False):
+        """src/sparseMatrix.cpp:1195-1220.  Returns evalues (float32[k], sigma^2 descending), or
+        (evalues, U[V,k]) with want_U.  Raises when nconv != k (the reference asserts, :1207)."""
+        k = int(num_topics)
+        ev = np.zeros(k, dtype=np.float32)
+        U = np.zeros((k, self._vocab_size), dtype=np.float32) if want_U else None
+        nconv = C.c_int()
+        self.ctx.call("isle_cuda_block_ks", k, int(block_size), int(max_iters), C.c_float(tol), int(seed),
+                      ptr(ev), ptr(U), C.byref(nconv))
+        self.U_cols = k
+        self.nconv = int(nconv.value)
+        return (ev, U.T.copy()) if want_U else ev
+
+    def set_U(self, U: np.ndarray) -> None:
+        """Harness hook: install U (V x k) computed elsewhere."""
+        U = np.asarray(U, dtype=np.float32)
+        self.U_cols = U.shape[1]
+        Uc = np.ascontiguousarray(U.T)
+        self.ctx.call("isle_cuda_set_U", int(self.U_cols), ptr(Uc))
+
+    def cleanup_after_eigensolver(self) -> None:
+        """src/sparseMatrix.cpp:1264-1275."""
+        self.ctx.call("isle_cuda_cleanup_eigensolver")
+
+    # -- stages D/E
+    def projected_docs(self) -> Tuple[np.ndarray, np.ndarray]:
+        """P = B^T U (D_B x k) and ||P_d||^2 (UT_times_docs / compute_projected_docs_l2sq)."""
+        P = np.zeros((self._num_docs, self.U_cols), dtype=np.float32)
+        l2 = np.zeros(self._num_docs, dtype=np.float32)
+        self.ctx.call("isle_cuda_project", ptr(P), ptr(l2))
+        return P, l2
+
+    def kmeans_init_on_projected_space(self, num_centers: int, max_reps: int = KMEANS_INIT_REPS, *, seed: int = 0):
+        """src/sparseMatrix.cpp:2212-2238.  Returns (best_seed u64[k], best_centers_coords f32[k,k],
+        min_total_dist)."""
+        k = int(num_centers)
+        best = None
+        for rep in range(max_reps):
+            seeds = np.zeros(k, dtype=np.uint64)
+            coords = np.zeros((k, k), dtype=np.float32)
+            res = C.c_float()
+            self.ctx.call("isle_cuda_kmeanspp", k, int(seed) + rep, ptr(seeds), ptr(coords), C.byref(res))
+            if best is None or res.value < best[2]:
+                best = (seeds, coords, float(res.value))
+        return best
+
+    def run_lloyds_on_projected_space(self, num_centers: int, projected_centers: np.ndarray,
+                                      closest_docs: Optional[List[list]] = None,
+                                      max_reps: int = MAX_KMEANS_LOWD_REPS):
+        """src/sparseMatrix.cpp:2016-2072.  ``projected_centers`` (k x k, center c = row c) is
+        updated in place; ``closest_docs`` (list of k lists) receives the partition when given.
+        Returns the residual the reference returns (always 0); the assignment,
+        objective and iteration count are kept in ``self.last_lloyd``."""
+        k = int(num_centers)
+        assert projected_centers.dtype == np.float32 and projected_centers.flags["C_CONTIGUOUS"]
+        assign = np.zeros(self._num_docs, dtype=np.uint32)
+        obj, iters = C.c_double(), C.c_int()
+        self.ctx.call("isle_cuda_lloyd_projected", k, ptr(projected_centers), int(max_reps), ptr(assign),
+                      C.byref(obj), C.byref(iters))
+        self.last_lloyd = dict(assign=assign, objective=float(obj.value), iters=int(iters.value))
+        if closest_docs is not None:
+            order = np.argsort(assign, kind="stable")
+            bounds = np.searchsorted(assign[order], np.arange(k + 1))
+            for c in range(k):
+                closest_docs[c][:] = order[bounds[c]:bounds[c + 1]].tolist()
+        return 0.0
+
+    def projected_closest_centers(self, num_centers: int, projected_centers: np.ndarray) -> np.ndarray:
+        """src/sparseMatrix.cpp:1852-1871 for all docs: argmin |dist|, first index on ties."""
+        assign = np.zeros(self._num_docs, dtype=np.uint32)
+        pc = np.ascontiguousarray(projected_centers, dtype=np.float32)
+        self.ctx.call("isle_cuda_assign_projected", int(num_centers), ptr(pc), ptr(assign))
+        return assign
+
+    def left_multiply_by_U_Spectra(self, inp: np.ndarray, ld_in: int, ncols: int) -> np.ndarray:
+        """src/sparseMatrix.cpp:1438-1450: out (V x ncols) = U * in, ``inp`` holds ncols columns of
+        length ld_in (column c = inp[c, :]).  Returns out with out[:, c] the lifted column."""
+        a = np.ascontiguousarray(inp, dtype=np.float32)
+        out = np.zeros((int(ncols), self._vocab_size), dtype=np.float32)
+        self.ctx.call("isle_cuda_lift_centers", int(ncols), ptr(a), int(ld_in), ptr(out))
+        return out.T.copy()

@@ -62,8 +62,8 @@ def threshold_counts(nz_docs: int, k: int):
 
 def round_half_away(x):
     """std::round on float (src/sparseMatrix.cpp:381,1344): half away from zero."""
-    x = np.asarray(x, dtype=F32)
-    return (np.sign(x) * np.floor(np.abs(x) + F32(0.5))).astype(F32)
+    x = np.asarray(x, dtype=F32).astype(np.float64)   # |x| + 0.5 is exact in double for fp32 x
+    return (np.sign(x) * np.floor(np.abs(x) + 0.5)).astype(F32)
 
 
 def compute_thresholds(vals, rows, V: int, nz_docs: int, k: int):

@@ -1,0 +1,300 @@
+"""GPU parity suite (-m gpu): every call goes through the C ABI of libisle_cuda.so (via the
+host mirror isle_b200.sparse_matrix) and is checked against the oracle and the golden
+fixtures.  Bars (BASELINE.json north star): thresholds and B bit-exact; singular values
+within 1e-4 relative, principal angle < 1e-3; identical Lloyd assignments from identical
+projection and initial centers (ties excepted); objective within 1e-4."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import isle_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(*arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def make_AB(ctx, V, D, k, vals, rows, offsets, avg, nz, mask=None):
+    from isle_b200.sparse_matrix import FPSparseMatrix, SparseMatrix
+    A = SparseMatrix(V, D, ctx)
+    A.populate_normalized(vals, rows, offsets, avg, nz)
+    zetas, nn = A.compute_thresholds(0, V, A.list_word_freqs_by_sorting(), k)
+    B = FPSparseMatrix(A)
+    if mask is None:
+        oc = B.threshold_and_copy(A, zetas, nn)
+    else:
+        oc = B.sampled_threshold_and_copy(A, zetas, nn, 0.0, select_docs=mask)
+    return A, B, zetas, nn, oc
+
+
+def tiny_AB(ctx, g, mask=None):
+    return make_AB(ctx, int(g["V"]), int(g["D"]), int(g["k"]), g["A_normalized_vals"], g["rows"], g["offsets"],
+                   float(g["avg_doc_sz"]), int(g["D"]), mask)
+
+
+# ---------------------------------------------------------------- family (1): bit-exact
+def test_thresholds_and_B_bit_exact_tiny(ctx, golden_tiny):
+    g = golden_tiny
+    A, B, zetas, nn, oc = tiny_AB(ctx, g)
+    assert np.array_equal(zetas, g["zetas"])
+    assert nn == int(g["new_nnzs"])
+    vals, rows, offs, oc2 = B.download()
+    assert np.array_equal(vals, g["B_vals"])
+    assert np.array_equal(rows, g["B_rows"].astype(np.uint64))
+    assert np.array_equal(offs, g["B_offsets"])
+    assert np.array_equal(oc, g["B_original_cols"].astype(np.uint64)) and np.array_equal(oc, oc2)
+    assert abs(B.frobenius() - float(g["frobenius"])) <= 1e-6 * float(g["frobenius"])
+
+
+def test_u64_upload_path(ctx, golden_tiny):
+    g = dict(golden_tiny)
+    g["rows"] = g["rows"].astype(np.uint64)           # the reference's own index width
+    A, B, zetas, nn, oc = tiny_AB(ctx, g)
+    assert np.array_equal(zetas, g["zetas"]) and B.get_nnzs() == int(g["nnz_B"])
+
+
+def test_masked_B_bit_exact(ctx, golden_tiny, golden_tiny_masked):
+    g, m = golden_tiny, golden_tiny_masked
+    A, B, zetas, nn, oc = tiny_AB(ctx, g, mask=m["mask"])
+    vals, rows, offs, oc2 = B.download()
+    assert np.array_equal(vals, m["B_vals"]) and np.array_equal(rows, m["B_rows"].astype(np.uint64))
+    assert np.array_equal(offs, m["B_offsets"]) and np.array_equal(oc2, m["B_original_cols"].astype(np.uint64))
+
+
+def test_c1_thresholds_and_B_bit_exact(ctx, golden_c1, corpus_c1):
+    g, c = golden_c1, corpus_c1
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    A, B, zetas, nn, oc = make_AB(ctx, c.V, c.D, c.k, vals, c.rows, c.offsets, avg, nz)
+    assert np.array_equal(zetas, g["zetas"]) and nn == int(g["new_nnzs"])
+    bv, br, bo, boc = B.download()
+    assert sha(bv, br.astype(np.uint32), bo, boc.astype(np.uint32)) == str(g["B_sha"])
+
+
+def test_sampling_weights(ctx, golden_tiny):
+    g = golden_tiny
+    A, B, zetas, nn, oc = tiny_AB(ctx, g)
+    w = np.zeros(int(g["D"]), np.float32)
+    from isle_b200._capi import ptr
+    ctx.call("isle_cuda_sampling_weights", ptr(w))
+    assert np.array_equal(w, O.sampling_weights(g["A_normalized_vals"], g["rows"], g["offsets"], g["zetas"]))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_thresholds_ragged_edge_cases(ctx, seed):
+    """Empty docs, absent words, one-word docs, values that round to zero, heavy ties."""
+    rng = np.random.default_rng(seed)
+    V, D, k = 257, 1203, 10
+    lens = rng.integers(0, 40, size=D)
+    lens[rng.random(D) < 0.1] = 0                       # empty docs
+    lens[:5] = [0, 1, 1, 0, 39]
+    rows, counts = [], []
+    for L in lens:
+        w = np.sort(rng.choice(V - 7, size=L, replace=False))     # last 7 words never occur
+        rows.append(w)
+        counts.append(rng.choice([1, 1, 1, 2, 3, 7, 30], size=L))
+    offsets = np.zeros(D + 1, np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    rows = np.concatenate(rows).astype(np.uint32)
+    counts = np.concatenate(counts).astype(np.uint32)
+    vals, avg, nz = O.normalize_docs(counts, offsets)
+    z_ref, nn_ref = O.compute_thresholds(vals, rows, V, nz, k)
+    bv, br, bo, oc = O.threshold_and_copy(vals, rows, offsets, z_ref)
+    A, B, zetas, nn, goc = make_AB(ctx, V, D, k, vals, rows, offsets, avg, nz)
+    assert np.array_equal(zetas, z_ref) and nn == nn_ref
+    gv, gr, go, goc2 = B.download()
+    assert np.array_equal(gv, bv) and np.array_equal(gr, br.astype(np.uint64))
+    assert np.array_equal(go, bo) and np.array_equal(goc, oc.astype(np.uint64))
+    assert B.num_docs() == len(oc) < D                   # some docs were dropped
+
+
+def test_value_above_avg_doc_sz_is_rejected(ctx):
+    """The reference asserts value <= avg_doc_sz (src/sparseMatrix.cpp:380); we fail loudly."""
+    from isle_b200._capi import IsleCudaError
+    from isle_b200.sparse_matrix import SparseMatrix
+    A = SparseMatrix(4, 2, ctx)
+    A.populate_normalized(np.array([50.0, 1.0], np.float32), np.array([0, 1], np.uint32),
+                          np.array([0, 1, 2], np.int64), 3.0, 2)
+    with pytest.raises(IsleCudaError):
+        A.compute_thresholds(0, 4, None, 2)
+
+
+# ---------------------------------------------------------------- family (2): the operator
+@pytest.mark.parametrize("b", [1, 4, 10, 16])
+def test_spsptr_multiply_matches_oracle(ctx, golden_tiny, b):
+    g = golden_tiny
+    A, B, *_ = tiny_AB(ctx, g)
+    Bo = O.to_csc(g["B_vals"], g["B_rows"], g["B_offsets"], int(g["V"]))
+    X = np.random.default_rng(b).standard_normal((int(g["V"]), b)).astype(np.float32)
+    Z = B.multiply(X)
+    Zr = (Bo @ (Bo.T @ X.astype(np.float64)))
+    assert np.max(np.abs(Z - Zr)) <= 2e-6 * np.max(np.abs(Zr))
+
+
+def test_spsptr_multiply_c1_split_rows(ctx, golden_c1, corpus_c1):
+    """c1 has word rows longer than one work item (split + atomics path) ."""
+    g, c = golden_c1, corpus_c1
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    A, B, zetas, nn, oc = make_AB(ctx, c.V, c.D, c.k, vals, c.rows, c.offsets, avg, nz)
+    bv, br, bo, _ = O.threshold_and_copy(vals, c.rows, c.offsets, g["zetas"])
+    Bo = O.to_csc(bv, br, bo, c.V)
+    assert np.diff(Bo.tocsr().indptr).max() > 2048
+    X = np.random.default_rng(0).standard_normal((c.V, 10)).astype(np.float32)
+    Z = B.multiply(X)
+    Zr = (Bo @ (Bo.T @ X.astype(np.float64)))
+    assert np.max(np.abs(Z - Zr)) <= 5e-6 * np.max(np.abs(Zr))
+    # linearity (size independent property)
+    Z2 = B.multiply(2.0 * X + 1.0)
+    Z1 = B.multiply(np.ones_like(X))
+    assert np.max(np.abs(Z2 - (2 * Z + Z1))) <= 1e-4 * np.max(np.abs(Z2))
+
+
+# ---------------------------------------------------------------- stage C: eigenpairs
+def check_eigs(ev, U, ev_ref, U_ref, frob):
+    k = len(ev)
+    s, s_ref = np.sqrt(ev), np.sqrt(ev_ref)
+    assert np.all(np.diff(ev) <= 1e-3 * ev[:-1])                       # descending
+    assert np.max(np.abs(s - s_ref) / s_ref) < 1e-4                    # singular values
+    assert O.principal_angle_sin(U, U_ref) < 1e-3                      # principal subspace
+    assert np.linalg.norm(U.T.astype(np.float64) @ U - np.eye(k)) < 1e-4
+    assert ev.sum() <= frob * (1 + 1e-6)
+
+
+def test_block_ks_tiny(ctx, golden_tiny):
+    g = golden_tiny
+    k, V = int(g["k"]), int(g["V"])
+    A, B, *_ = tiny_AB(ctx, g)
+    B.initialize_for_eigensolver(k)
+    ev, U = B.compute_block_ks(k, seed=1, want_U=True)
+    assert B.nconv == k
+    check_eigs(ev, U, g["evalues"], g["U_colmajor"].reshape(k, V).T, float(g["frobenius"]))
+    # residual check against the operator itself: ||B B^T u - lambda u|| <= tol * lambda
+    Z = B.multiply(U[:, :10].copy())
+    r = np.linalg.norm(Z - U[:, :10] * ev[:10], axis=0) / ev[:10]
+    assert r.max() < 5e-4
+
+
+def test_block_ks_c1(ctx, golden_c1, corpus_c1):
+    g, c = golden_c1, corpus_c1
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    A, B, *_ = make_AB(ctx, c.V, c.D, c.k, vals, c.rows, c.offsets, avg, nz)
+    ev, U = B.compute_block_ks(c.k, seed=2, want_U=True)
+    check_eigs(ev, U, g["evalues"], g["U_colmajor"].reshape(c.k, c.V).T, float(g["frobenius"]))
+
+
+def test_block_ks_rejects_bad_k(ctx, golden_tiny):
+    from isle_b200._capi import IsleCudaError
+    A, B, *_ = tiny_AB(ctx, golden_tiny)
+    with pytest.raises(IsleCudaError):
+        B.compute_block_ks(15)          # reference would write V out of bounds (k % b != 0)
+
+
+# ---------------------------------------------------------------- family (3): k-means
+def setup_projection(ctx, g):
+    k, V = int(g["k"]), int(g["V"])
+    A, B, *_ = tiny_AB(ctx, g)
+    U_ref = g["U_colmajor"].reshape(k, V).T.copy()
+    B.set_U(U_ref)
+    Bo = O.to_csc(g["B_vals"], g["B_rows"], g["B_offsets"], V)
+    return B, O.project(Bo, U_ref), k
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+def test_projection_and_assignment_match_oracle(ctx, golden_tiny, engine):
+    g = golden_tiny
+    ctx.set_option("dist_kernel", engine)
+    B, P_ref, k = setup_projection(ctx, g)
+    P, l2 = B.projected_docs()
+    assert np.max(np.abs(P - P_ref)) <= 1e-5 * np.max(np.abs(P_ref))
+    assert np.allclose(l2, O.docs_l2sq(P_ref), rtol=1e-5)
+    C0 = g["centers_lowd_init"].reshape(k, k)
+    a = B.projected_closest_centers(k, C0)
+    a_ref = O.closest_centers(P_ref, O.docs_l2sq(P_ref), C0)
+    assert int((a != a_ref).sum()) == 0
+    ctx.set_option("dist_kernel", 1)
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+def test_lloyd_matches_reference(ctx, golden_tiny, engine):
+    g = golden_tiny
+    ctx.set_option("dist_kernel", engine)
+    B, P_ref, k = setup_projection(ctx, g)
+    C = g["centers_lowd_init"].reshape(k, k).copy()
+    closest = [[] for _ in range(k)]
+    B.run_lloyds_on_projected_space(k, C, closest, 10)
+    a = B.last_lloyd["assign"]
+    assert np.array_equal(a, g["lloyd_assign"])                       # identical partition
+    assert sorted(sum(closest, [])) == list(range(B.num_docs()))
+    Cr = g["centers_lowd_final"].reshape(k, k)
+    assert np.max(np.abs(C - Cr)) < 1e-4
+    obj_ref = O.kmeans_objective(P_ref, Cr, g["lloyd_assign"])
+    assert abs(B.last_lloyd["objective"] - obj_ref) / obj_ref < 1e-4
+    lifted = B.left_multiply_by_U_Spectra(C, k, k)
+    assert np.max(np.abs(lifted - O.lift_centers(g["U_colmajor"].reshape(k, int(g["V"])).T, C))) < 1e-4
+    ctx.set_option("dist_kernel", 1)
+
+
+def test_lloyd_c1_matches_reference(ctx, golden_c1, corpus_c1):
+    g, c = golden_c1, corpus_c1
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    A, B, *_ = make_AB(ctx, c.V, c.D, c.k, vals, c.rows, c.offsets, avg, nz)
+    B.set_U(g["U_colmajor"].reshape(c.k, c.V).T.copy())
+    C = g["centers_lowd_init"].reshape(c.k, c.k).copy()
+    B.run_lloyds_on_projected_space(c.k, C, None, 10)
+    mism = int((B.last_lloyd["assign"] != g["lloyd_assign"]).sum())
+    assert mism <= 2, mism                                           # ties excepted
+    assert np.max(np.abs(C - g["centers_lowd_final"].reshape(c.k, c.k))) < 1e-3
+
+
+def test_empty_cluster_center_stays_zero(ctx, golden_tiny):
+    """src/sparseMatrix.cpp:1988-1992."""
+    g = golden_tiny
+    B, P_ref, k = setup_projection(ctx, g)
+    C = g["centers_lowd_init"].reshape(k, k).copy()
+    C[3] = 1e6                                           # nobody is closest to this center
+    B.run_lloyds_on_projected_space(k, C, None, 1)
+    assert np.all(C[3] == 0.0)
+    assert not np.any(B.last_lloyd["assign"] == 3)
+
+
+def test_kmeanspp_invariants(ctx, golden_tiny):
+    g = golden_tiny
+    B, P_ref, k = setup_projection(ctx, g)
+    seeds, coords, res = B.kmeans_init_on_projected_space(k, 1, seed=11)
+    assert len(set(seeds.tolist())) == k                 # no replicated center (:2176-2178)
+    assert np.max(np.abs(coords - P_ref[seeds.astype(np.int64)])) <= 1e-5 * np.max(np.abs(P_ref))
+    assert res > 0
+    # D^2 seeding must beat uniform seeding on the k-means++ potential, on average
+    d2 = O.docs_l2sq(P_ref)
+    pot = lambda S: np.maximum(O.dist_matrix(P_ref, d2, P_ref[S]), 0).min(1).sum()
+    rng = np.random.default_rng(0)
+    uni = np.mean([pot(rng.choice(len(P_ref), k, replace=False)) for _ in range(8)])
+    assert pot(seeds.astype(np.int64)) < uni
+
+
+# ---------------------------------------------------------------- end to end
+def test_spectral_core_end_to_end_c1(ctx, golden_c1, corpus_c1):
+    """Stages A-E through the public call; k-means is checked through rotation-invariant
+    quantities because our U spans the same subspace as the reference's but is not identical."""
+    from isle_b200.trainer import spectral_core
+    g, c = golden_c1, corpus_c1
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    r = spectral_core(ctx, c.V, c.D, c.k, vals, c.rows, c.offsets, avg, nz, seed=4, want_U=True)
+    assert np.array_equal(r.zetas, g["zetas"]) and r.nnz_B == int(g["nnz_B"]) and r.D_B == int(g["D_B"])
+    U_ref = g["U_colmajor"].reshape(c.k, c.V).T
+    s, s_ref = np.sqrt(r.evalues), np.sqrt(g["evalues"])
+    assert np.max(np.abs(s - s_ref) / s_ref) < 1e-4
+    assert O.principal_angle_sin(r.U, U_ref) < 1e-3
+    # oracle Lloyd from OUR seeds on the oracle's projection (distances are rotation invariant)
+    bv, br, bo, _ = O.threshold_and_copy(vals, c.rows, c.offsets, g["zetas"])
+    P_ref = O.project(O.to_csc(bv, br, bo, c.V), U_ref)
+    C_ref, a_ref, _ = O.run_lloyds(P_ref, P_ref[r.seeds.astype(np.int64)], 10)
+    obj_ref = O.kmeans_objective(P_ref, C_ref, a_ref)
+    assert abs(r.objective - obj_ref) / obj_ref < 2e-3
+    assert r.centers.shape == (c.V, c.k)
+    assert ctx.stat("launches") > 0

@@ -1,0 +1,231 @@
+"""CPU suite: pins the numpy oracle (oracle/isle_oracle.py) against fixtures produced by the
+UNMODIFIED reference compiled in-container (tests/golden/make_golden.py), checks the rule on
+hand-made edge cases, and checks that the C-ABI library loads and exports every symbol that
+include/isle_cuda.h declares (no compute calls: there is no GPU here)."""
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import isle_oracle as O
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def sha(*arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+# ------------------------------------------------------------------ golden: stages 0/A/B
+def test_normalize_matches_reference(golden_tiny):
+    g = golden_tiny
+    vals, avg, nz = O.normalize_docs(g["counts"], g["offsets"])
+    assert avg == g["avg_doc_sz"]
+    assert np.array_equal(vals, g["A_normalized_vals"])        # bit-exact
+
+
+def test_thresholds_and_B_bit_exact_tiny(golden_tiny):
+    g = golden_tiny
+    vals, avg, nz = O.normalize_docs(g["counts"], g["offsets"])
+    z, nn = O.compute_thresholds(vals, g["rows"], int(g["V"]), nz, int(g["k"]))
+    assert np.array_equal(z, g["zetas"])
+    assert nn == int(g["new_nnzs"])
+    bv, br, bo, oc = O.threshold_and_copy(vals, g["rows"], g["offsets"], z)
+    assert np.array_equal(bv, g["B_vals"]) and np.array_equal(br, g["B_rows"])
+    assert np.array_equal(bo, g["B_offsets"]) and np.array_equal(oc, g["B_original_cols"])
+    assert len(oc) == int(g["D_B"]) and bo[-1] == int(g["nnz_B"]) == nn
+
+
+def test_masked_B_bit_exact(golden_tiny, golden_tiny_masked):
+    g, m = golden_tiny, golden_tiny_masked
+    bv, br, bo, oc = O.threshold_and_copy(g["A_normalized_vals"], g["rows"], g["offsets"], g["zetas"],
+                                          select_docs=m["mask"].astype(bool))
+    assert np.array_equal(bv, m["B_vals"]) and np.array_equal(br, m["B_rows"])
+    assert np.array_equal(bo, m["B_offsets"]) and np.array_equal(oc, m["B_original_cols"])
+
+
+def test_c1_thresholds_and_B_digest(golden_c1, corpus_c1):
+    """BASELINE.json configs[0] shape: 10k docs x 5k vocab, k=20."""
+    g, c = golden_c1, corpus_c1
+    assert sha(c.offsets, c.rows, c.counts) == str(g["corpus_sha"]), "corpus generator drifted"
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    assert sha(vals) == str(g["A_vals_sha"])
+    z, nn = O.compute_thresholds(vals, c.rows, c.V, nz, c.k)
+    assert np.array_equal(z, g["zetas"]) and nn == int(g["new_nnzs"])
+    bv, br, bo, oc = O.threshold_and_copy(vals, c.rows, c.offsets, z)
+    assert sha(bv, br, bo, oc) == str(g["B_sha"])
+
+
+# ------------------------------------------------------------------ threshold rule edge cases
+def _rule(values_per_word, nz_docs, k):
+    rows, vals = [], []
+    for w, vs in enumerate(values_per_word):
+        rows += [w] * len(vs)
+        vals += list(vs)
+    z, nn = O.compute_thresholds(np.array(vals, np.float32), np.array(rows, np.uint32), len(values_per_word),
+                                 nz_docs, k)
+    return z.tolist(), nn
+
+
+def test_threshold_rule_edges():
+    # count_gr = 100/(2*5) = 10 ; count_eq = ceil(0.05*100/5) = 1
+    assert O.threshold_counts(100, 5) == (10, 1)
+    # evaluated in double exactly as the C expression (3.0 * (1.0/60.0) * nz / k, then ceil)
+    assert O.threshold_counts(9999, 20) == (249, 25)
+    assert O.threshold_counts(10000, 20) == (250, 25)
+    assert O.threshold_counts(1, 2000) == (1, 1)
+    z, nn = _rule([[], [3.0] * 4, [0.2, 0.4]], 100, 5)
+    assert z == [1.0, 1.0, 1.0]            # absent word / fewer than count_gr values / all round to 0
+    assert nn == 4
+    # count_gr=2, count_eq=3 (nz=20,k=5 -> gr=2, eq=ceil(0.2...)=1) choose sizes explicitly instead:
+    gr, eq = O.threshold_counts(60, 5)      # (6, 1)
+    assert (gr, eq) == (6, 1)
+    # eq == 1: every candidate has >= 1 equal value, so the walk always falls to keep-all
+    z, nn = _rule([[9, 8, 7, 6, 5, 4, 3, 2]], 60, 5)
+    assert z == [1.0] and nn == 8
+    gr, eq = O.threshold_counts(400, 5)     # (40, 4)
+    vals = [10.0] * 39 + [7.0] * 3 + [5.0] * 10
+    z, nn = _rule([vals], 400, 5)           # 40th largest = 7 with 3 < 4 equal -> zeta 7, keep 42
+    assert z == [7.0] and nn == 42
+    vals = [10.0] * 39 + [7.0] * 4 + [5.0] * 2 + [1.0] * 9
+    z, nn = _rule([vals], 400, 5)           # 7 has 4 >= 4 -> next 5 (2 < 4) -> zeta 5, keep 45
+    assert z == [5.0] and nn == 45
+    vals = [10.0] * 39 + [7.0] * 4 + [5.0] * 4
+    z, nn = _rule([vals], 400, 5)           # walk runs off the smallest value -> keep all
+    assert z == [1.0] and nn == 47
+    vals = [2.5] * 50                        # round half away from zero -> 3
+    z, nn = _rule([vals], 400, 5)
+    assert z == [1.0] and nn == 50
+
+
+def test_round_half_away():
+    x = np.array([0.5, 1.5, 2.5, 0.49999997, 2.4999998, 7.0], np.float32)
+    assert O.round_half_away(x).tolist() == [1.0, 2.0, 3.0, 0.0, 2.0, 7.0]
+
+
+# ------------------------------------------------------------------ golden: stage C
+def test_block_ks_matches_reference(golden_tiny):
+    g = golden_tiny
+    V, k = int(g["V"]), int(g["k"])
+    B = O.to_csc(g["B_vals"], g["B_rows"], g["B_offsets"], V)
+    ev, U, nconv, ks = O.block_ks(B, k, seed=3)
+    assert nconv == k
+    s, s_ref = np.sqrt(ev), np.sqrt(g["evalues"])
+    assert np.max(np.abs(s - s_ref) / s_ref) < 1e-4                  # north-star tolerance
+    U_ref = g["U_colmajor"].reshape(k, V).T
+    assert O.principal_angle_sin(U, U_ref) < 1e-3
+    assert np.linalg.norm(U.T @ U - np.eye(k)) < 1e-4
+    assert ev.sum() <= float(g["frobenius"]) * (1 + 1e-6)            # sum sigma^2 <= ||B||_F^2
+
+
+def test_block_ks_planted_spectrum():
+    """Known-answer test in the spirit of block-ks/ks_utils.h:136-182 (dense operator with a
+    planted Zipf / sqrt-Zipf / linear spectrum)."""
+    rng = np.random.default_rng(0)
+    n, k = 300, 20
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    for kind in (1, 2, 3):
+        i = np.arange(n, dtype=np.float64)
+        ev = {1: 1.0 / (i + 1), 2: 1.0 / np.sqrt(i + 1), 3: (n - i) / n}[kind]
+        A = ((Q * ev) @ Q.T).astype(np.float32)
+        ks = O.BlockKS(lambda X: (A @ X).astype(np.float32), n, k, 2 * k + 10, 100, 10, 1e-4, seed=kind)
+        ks.init()
+        assert ks.compute() == k
+        got = ks.eigenvalues()
+        assert np.max(np.abs(got - ev[:k]) / ev[:k]) < 2e-4
+        assert O.principal_angle_sin(ks.eigenvectors(), Q[:, :k]) < 5e-2 if kind == 3 else True
+
+
+def test_compute_qr_rank_revealing():
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((500, 10)).astype(np.float32)
+    A[:, 4] = A[:, 1]                                    # exactly dependent column
+    Q, R, rank = O.compute_qr(A)
+    assert rank == 9 and Q.shape == (500, 9) and R.shape == (9, 10)
+    assert np.linalg.norm(Q.T @ Q - np.eye(9)) < 1e-5
+    assert np.linalg.norm(Q @ R - A) / np.linalg.norm(A) < 1e-5
+
+
+# ------------------------------------------------------------------ golden: stages D/E
+def test_lloyd_matches_reference(golden_tiny):
+    g = golden_tiny
+    V, k = int(g["V"]), int(g["k"])
+    B = O.to_csc(g["B_vals"], g["B_rows"], g["B_offsets"], V)
+    U_ref = g["U_colmajor"].reshape(k, V).T
+    P = O.project(B, U_ref)
+    C0 = g["centers_lowd_init"].reshape(k, k)
+    assert np.allclose(P[g["seeds"].astype(np.int64)], C0, atol=1e-5)   # seeds' coordinates = U^T doc
+    C, a, iters = O.run_lloyds(P, C0, 10)
+    assert np.array_equal(a, g["lloyd_assign"])
+    Cr = g["centers_lowd_final"].reshape(k, k)
+    assert np.max(np.abs(C - Cr)) < 1e-4
+    o1, o2 = O.kmeans_objective(P, C, a), O.kmeans_objective(P, Cr, g["lloyd_assign"])
+    assert abs(o1 - o2) / o2 < 1e-4
+
+
+def test_lloyd_c1_matches_reference(golden_c1, corpus_c1):
+    g, c = golden_c1, corpus_c1
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    bv, br, bo, oc = O.threshold_and_copy(vals, c.rows, c.offsets, g["zetas"])
+    B = O.to_csc(bv, br, bo, c.V)
+    U_ref = g["U_colmajor"].reshape(c.k, c.V).T
+    P = O.project(B, U_ref)
+    C, a, iters = O.run_lloyds(P, g["centers_lowd_init"].reshape(c.k, c.k), 10)
+    mism = int((a != g["lloyd_assign"]).sum())
+    assert mism <= 2, mism                                   # ties excepted
+    ev, U, nconv, _ = O.block_ks(B, c.k, seed=5)
+    s, s_ref = np.sqrt(ev), np.sqrt(g["evalues"])
+    assert nconv == c.k and np.max(np.abs(s - s_ref) / s_ref) < 1e-4
+    assert O.principal_angle_sin(U, U_ref) < 1e-3
+
+
+def test_kmeanspp_invariants(golden_tiny):
+    g = golden_tiny
+    V, k = int(g["V"]), int(g["k"])
+    B = O.to_csc(g["B_vals"], g["B_rows"], g["B_offsets"], V)
+    P = O.project(B, g["U_colmajor"].reshape(k, V).T)
+    seeds, C = O.kmeanspp(P, k, np.random.default_rng(0))
+    assert len(set(seeds.tolist())) == k                     # no duplicates (:2176-2178)
+    assert np.array_equal(C, P[seeds])
+
+
+def test_abs_argmin_first_index():
+    """cblas_isamin semantics: min |x|, first index on ties."""
+    P = np.array([[1.0, 0.0]], np.float32)
+    C = np.array([[1.0, 0.0], [1.0, 0.0], [0.0, 1.0]], np.float32)
+    assert O.closest_centers(P, O.docs_l2sq(P), C).tolist() == [0]
+
+
+# ------------------------------------------------------------------ the boundary
+def test_capi_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "isle_cuda.h")).read()
+    declared = sorted(set(re.findall(r"\b(isle_cuda_[A-Za-z0-9_]+)\s*\(", hdr)))
+    from isle_b200 import _capi
+    assert declared == _capi.EXPORTS, (set(declared) ^ set(_capi.EXPORTS))
+    for name in declared:
+        assert hasattr(_capi.lib, name)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from isle_b200 import _capi
+    with pytest.raises(_capi.IsleCudaError) as e:
+        _capi.Context(0)
+    assert e.value.code == _capi.ISLE_ERR_NOGPU
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "isle_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "isle_oracle" not in src and "oracle/" not in src.replace("oracle/ref_dump", ""), f
