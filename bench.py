@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- ISLETrain spectral core (threshold -> block-KS SVD -> k-means on the projection)
+docs/sec on N B200s, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--impl ours|reference]
+
+A "step" is one pass of stages A-E of ISLETrainer::train() (reference src/trainer.cpp:430-554)
+over one synthetic corpus.  At N=1 the corpus is BASELINE.json configs[1] (NYTimes-shaped:
+300k docs x 102k vocab, ~70M nnz, k=100); at N>1 every rank holds one such shard of documents
+(weak scaling, vocabulary and k shared).
+
+  value     docs/sec with the normalised CSC of A already resident in HBM, timed with CUDA
+            events on the library's own stream, max over ranks
+  e2e       the same through the reference-facing C ABI with HOST buffers: upload of A
+            (pinned host memory, u64 row ids as the reference holds them) and download of
+            zetas, original_cols, eigenvalues and the lifted centers inside the timed region
+  roofline  the B*B^T*X SpMM passes: algorithmic bytes / CUDA-event time, against
+            the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the UNMODIFIED reference C++ (oracle/_ref/ref_dump: reference sources over
+            OpenBLAS + the MKL shim, not Intel MKL) on the host cores, on a bounded document
+            slice of the same corpus
+
+--impl reference times only that CPU arm and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ISLETrain spectral-core docs/sec (threshold -> block-KS SVD -> k-means on projection)"
+UNIT = "docs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample-docs", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="isle_clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            sm, mx, reasons = [], [], set()
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1])); mx.append(float(f[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                       "samples": len(sm)}
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_ref_dump(c, k, nthreads, workdir):
+    """Times the unmodified reference (oracle/_ref/ref_dump) on corpus `c`; returns stage seconds."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+    if not os.path.exists(exe):
+        raise RuntimeError("oracle/_ref/ref_dump missing (built by __graft_entry__.build() in the container)")
+    path = os.path.join(workdir, "corpus.bin")
+    c.write_bin(path)
+    env = dict(os.environ, OMP_THREAD_LIMIT=str(nthreads), OMP_NUM_THREADS=str(nthreads),
+               OPENBLAS_NUM_THREADS=str(nthreads))
+    t0 = time.perf_counter()
+    subprocess.run([exe, path, workdir, str(k)], check=True, env=env, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
+    wall = time.perf_counter() - t0
+    meta = json.load(open(os.path.join(workdir, "meta.json")))
+    core = sum(meta[x] for x in ("t_thresholds", "t_build_B", "t_block_ks", "t_kmeanspp", "t_lloyd"))
+    return core, wall, meta
+
+
+def slice_corpus(c, ndocs):
+    from isle_b200.corpus import Corpus
+    ndocs = min(ndocs, c.D)
+    e = int(c.offsets[ndocs])
+    return Corpus(c.V, ndocs, c.k, c.offsets[: ndocs + 1].copy(), c.rows[:e].copy(), c.counts[:e].copy())
+
+
+def make_corpus(name, rank, seed):
+    import torch
+    from isle_b200 import corpus
+    cfg = dict(corpus.CONFIGS[name])
+    backend = "torch" if (torch.cuda.is_available() and cfg["D"] * 50 > 2_000_000) else "numpy"
+    return corpus.generate(V=cfg["V"], D=cfg["D"], k=cfg["k"], mu=cfg["mu"], seed=cfg["seed"] + 1000 * rank + seed,
+                           backend=backend, device=f"cuda:{torch.cuda.current_device()}" if backend == "torch" else "cpu")
+
+
+def pinned(a: np.ndarray) -> np.ndarray:
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    try:
+        return t.pin_memory().numpy()
+    except Exception:
+        return t.numpy()
+
+
+# ------------------------------------------------------------------------------- reference arm
+def bench_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from isle_b200 import corpus
+    ncores = os.cpu_count() or 1
+    cfg = corpus.CONFIGS[args.config]
+    nsteps = args.steps + args.warmup
+    ndocs = args.cpu_sample_docs or max(4000, min(30000, int(30000 * 6 / max(nsteps, 1))))
+    ndocs = min(ndocs, cfg["D"])
+    c = corpus.generate(V=cfg["V"], D=ndocs, k=cfg["k"], mu=cfg["mu"], seed=cfg["seed"] + args.seed)
+    times = []
+    with tempfile.TemporaryDirectory(prefix="isle_ref_") as wd:
+        for i in range(nsteps):
+            core, wall, meta = run_ref_dump(c, cfg["k"], ncores, wd)
+            if i >= args.warmup:
+                times.append(core)
+    t = float(np.mean(times))
+    val = ndocs / t
+    sample = (f"{ndocs}-doc corpus of the {args.config} shape (V={cfg['V']}, k={cfg['k']}, "
+              f"{c.nnz} nnz), stages A-E, reference C++ over OpenBLAS + MKL shim (not Intel MKL)")
+    line = {
+        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"{args.config}: {cfg['D']} docs x {cfg['V']} vocab, k={cfg['k']}", "sample_docs": ndocs},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- our arm
+def bench_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from isle_b200 import _capi, corpus
+    from isle_b200._capi import ptr
+    from oracle import isle_oracle as O   # cpu_baseline leg + input normalisation only
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(_capi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+    ctx = _capi.Context(local, rank, world, nccl_id)
+
+    cfg = corpus.CONFIGS[args.config]
+    V, k = cfg["V"], cfg["k"]
+    c = make_corpus(args.config, rank, args.seed)
+    D, nnz = c.D, c.nnz
+    # input normalisation = ISLETrainer's own ingest (populate_CSC + normalize_docs), outside the path
+    if world > 1:
+        tot = torch.tensor([int(c.counts.astype(np.uint64).sum()), int((np.diff(c.offsets) > 0).sum())],
+                           dtype=torch.int64, device="cuda")
+        dist.all_reduce(tot)
+        avg = np.float32(int(tot[0].item()) // int(tot[1].item()))
+        lens = np.diff(c.offsets)
+        sums = np.add.reduceat(c.counts.astype(np.int64), c.offsets[:-1])
+        vals = (avg * (c.counts.astype(np.float32) / np.repeat(sums.astype(np.float32), lens))).astype(np.float32)
+        nz_local = int((lens > 0).sum())
+    else:
+        vals, avg, nz_local = O.normalize_docs(c.counts, c.offsets)
+    h_vals = pinned(vals)
+    h_rows64 = pinned(c.rows.astype(np.uint64))
+    h_offs = pinned(c.offsets.astype(np.int64))
+    torch.cuda.empty_cache()
+
+    zetas = np.zeros(V, np.float32)
+    evalues = np.zeros(k, np.float32)
+    seeds = np.zeros(k, np.uint64)
+    centers_lowd = np.zeros((k, k), np.float32)
+    centers = np.zeros((k, V), np.float32)
+    state = {}
+
+    def upload():
+        ctx.call("isle_cuda_upload_A", V, D, nnz, ptr(h_vals), ptr(h_rows64), ptr(h_offs), C.c_float(float(avg)), nz_local)
+
+    def core(host_outputs: bool, step_seed: int):
+        nn, nnzB, DB, nconv = C.c_int64(), C.c_int64(), C.c_uint64(), C.c_int()
+        res, obj, iters = C.c_float(), C.c_double(), C.c_int()
+        ctx.call("isle_cuda_thresholds", k, ptr(zetas) if host_outputs else None, C.byref(nn))
+        ctx.call("isle_cuda_build_B", None, C.byref(nnzB), C.byref(DB))
+        if host_outputs:
+            oc = np.zeros(int(DB.value), np.uint64)
+            ctx.call("isle_cuda_download_B", None, None, None, ptr(oc))
+        ctx.call("isle_cuda_block_ks", k, 10, 100, C.c_float(1e-4), step_seed, ptr(evalues), None, C.byref(nconv))
+        ctx.call("isle_cuda_kmeanspp", k, step_seed, ptr(seeds), ptr(centers_lowd), C.byref(res))
+        ctx.call("isle_cuda_lloyd_projected", k, ptr(centers_lowd), 10, None, C.byref(obj), C.byref(iters))
+        ctx.call("isle_cuda_lift_centers", k, ptr(centers_lowd), k, ptr(centers) if host_outputs else None)
+        ctx.call("isle_cuda_cleanup_eigensolver")
+        state.update(nnzB=int(nnzB.value), DB=int(DB.value), nconv=int(nconv.value), iters=int(iters.value),
+                     objective=float(obj.value))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: full end-to-end steps
+    for i in range(args.warmup):
+        upload()
+        core(True, args.seed + i)
+
+    # ---- (1) device-resident: A stays in HBM, CUDA events on the library stream
+    upload()
+    ctx.call("isle_cuda_reset_stats")
+    ctx.call("isle_cuda_set_profiling", 1)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ctx.call("isle_cuda_timer_start")
+    for i in range(args.steps):
+        core(False, args.seed + 100 + i)
+    ms = C.c_double()
+    ctx.call("isle_cuda_timer_stop", C.byref(ms))
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = ms.value
+    st = {n: ctx.stat(n) for n in ("launches", "spmm_bt_ms", "spmm_bt_bytes", "spmm_bt_calls", "spmm_b_ms",
+                                   "spmm_b_bytes", "spmm_b_calls", "ks_op_ms", "ks_orth_ms", "ks_qr_ms",
+                                   "ks_truncate_ms", "ks_restarts", "project_ms", "lloyd_iter_ms", "pp_round_ms",
+                                   "thr_hist_ms", "thr_zeta_ms", "b_count_ms", "b_compact_ms", "csr_build_ms",
+                                   "dist_tc_ms", "dist_simt_ms", "dist_tc_flops", "dist_simt_flops", "lloyd_accum_ms")}
+    ctx.call("isle_cuda_set_profiling", 0)
+
+    # ---- (2) end to end: host buffers in, host results out, every step
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        upload()
+        core(True, args.seed + 200 + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        tt = torch.tensor([dev_ms, e2e_s, float(D)], dtype=torch.float64, device="cuda")
+        tmax = tt.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tt.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s, total_docs = float(tmax[0]), float(tmax[1]), float(tsum[2])
+    else:
+        total_docs = float(D)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        spmm_ms = st["spmm_bt_ms"] + st["spmm_b_ms"]
+        spmm_bytes = st["spmm_bt_bytes"] + st["spmm_b_bytes"]
+        ach = spmm_bytes / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
+        ncalls = st["spmm_bt_calls"] + st["spmm_b_calls"]
+        h2d = nnz * (4 + 8) + (D + 1) * 8
+        d2h = V * 4 + state["DB"] * 8 + k * 4 + k * 8 + 2 * k * k * 4 + V * k * 4
+        line = {
+            "metric": METRIC, "value": total_docs * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config} NYTimes-shaped synthetic per GPU: {D} docs x {V} vocab, {nnz} nnz, k={k}",
+                       "block_size": 10, "tol": 1e-4, "l2": "inputs (A: %.0f MB) larger than the 126 MB L2" % (nnz * 8 / 1e6),
+                       "D_B": state["DB"], "nnz_B": state["nnzB"], "ks_restarts": st["ks_restarts"],
+                       "lloyd_iters": state["iters"], "nconv": state["nconv"]},
+            "e2e": {"value": total_docs * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(st["launches"]),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "spmm_gather_kernel (B^T X and B Y passes)", "achieved": ach,
+                         "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None, "traffic": None,
+                         "peak_source": peak_src, "launches": int(ncalls),
+                         "avg_launch_ms": spmm_ms / ncalls if ncalls else None,
+                         "bytes_per_launch": spmm_bytes / ncalls if ncalls else None},
+            "stage_ms_per_step": {n[:-3]: st[n] / args.steps for n in st if n.endswith("_ms")},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                ncores = os.cpu_count() or 1
+                nd = args.cpu_sample_docs or 30000
+                cs = slice_corpus(c, nd)
+                with tempfile.TemporaryDirectory(prefix="isle_ref_") as wd:
+                    core_s, wall, meta = run_ref_dump(cs, k, ncores, wd)
+                line["cpu_baseline"] = {
+                    "value": cs.D / core_s, "unit": UNIT, "cores": ncores, "kind": "reference",
+                    "sample": f"first {cs.D} docs of the same corpus ({cs.nnz} nnz, V={V}, k={k}), stages A-E in "
+                              f"{core_s:.1f} s; unmodified reference C++ over OpenBLAS + MKL shim (not Intel MKL)",
+                    "stage_s": {x: meta[x] for x in ("t_thresholds", "t_build_B", "t_block_ks", "t_kmeanspp", "t_lloyd")}}
+            except Exception as e:  # the baseline is reported, never allowed to sink the bench line
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                                        "sample": f"unavailable: {e}"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        bench_reference(a)
+    else:
+        bench_ours(a)

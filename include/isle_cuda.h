@@ -121,7 +121,8 @@ int isle_cuda_lloyd_projected(isle_cuda_ctx *ctx, uint64_t k, float *centers_low
 int isle_cuda_assign_projected(isle_cuda_ctx *ctx, uint64_t k, const float *centers_lowd,
                                uint32_t *assign_out);
 /* Replaces left_multiply_by_U_Spectra (src/sparseMatrix.cpp:1438-1450):
- * centers_out (V x ncols, column-major) = U * in (k x ncols column-major, leading dim ld_in). */
+ * centers_out (V x ncols, column-major) = U * in (k x ncols column-major, leading dim ld_in).
+ * centers_out may be NULL (product computed, result left on the device: device-only timing). */
 int isle_cuda_lift_centers(isle_cuda_ctx *ctx, uint64_t ncols, const float *in, uint64_t ld_in,
                            float *centers_out);
 /* cleanup_after_eigensolver (src/sparseMatrix.cpp:1264-1275): frees U, P and solver state. */
