@@ -20,6 +20,7 @@ namespace cg = cooperative_groups;
 namespace isle {
 
 static constexpr int kMaxB = 16;
+static constexpr int kCholDynSmem = 16 * 256 * 8;   // cholqr2_kernel reduction scratch
 
 // ------------------------------------------------------------------------------- helpers
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
@@ -226,12 +227,296 @@ mgs_qr64_kernel(QrParams p)
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.rank_out = rank;
 }
 
+
+// ------------------------------------------------------------------- CholeskyQR2 (fp64)
+// Fast path of compute_qr (block-ks/ks_utils.h:43-127) for a numerically full-rank block:
+//   G1 = F^T F, R1 = chol(G1);  G2 = (F R1^-1)^T (F R1^-1), R2 = chol(G2);
+//   Q = F (R1^-1 R2^-1) rounded to fp32, R = R2 R1,
+// all in fp64 with fixed-order grid reductions (bitwise reproducible, so replicated ranks
+// stay in lock step).  One cooperative launch, two grid barriers.  When a Cholesky pivot
+// falls under the reference's rank cut (column norm < 1e-6, ks_utils.h:69) or under the
+// fp64 noise floor of the Gram matrix, rank_out = -1 and the caller runs the rank-revealing
+// MGS kernel above, which follows the reference step by step.
+struct CholQrParams {
+    const float *F;      // n x b, column-major, ld = n
+    int64_t n;
+    int b;
+    float *Q;            // n x b out (ld = n)
+    float *R;            // b x b column-major out
+    int *rank_out;       // b, or -1 = fall back to mgs_qr64_kernel
+    double *part;        // gridDim.x x 256 partial Gram sums
+};
+
+// Gram partials of this block's rows of X = F * T (T upper triangular b x b in smem, or
+// identity when T == nullptr).  Thread (p = tid & 15, r = tid >> 4) owns row r of each
+// 16-row tile and column p of the Gram matrix.
+__device__ __forceinline__ void gram_partial(const CholQrParams &p, const double (*T)[kMaxB], double (*xs)[kMaxB + 1],
+                                             double (*ys)[kMaxB + 1], double *red, double *dst)
+{
+    const int pc = threadIdx.x & 15, r = threadIdx.x >> 4;
+    const int b = p.b;
+    double acc[kMaxB];
+#pragma unroll
+    for (int q = 0; q < kMaxB; ++q) acc[q] = 0.0;
+    for (int64_t row0 = (int64_t)blockIdx.x * 16; row0 < p.n; row0 += (int64_t)gridDim.x * 16) {
+        const int64_t row = row0 + r;
+        xs[r][pc] = (row < p.n && pc < b) ? (double)p.F[row + (size_t)pc * p.n] : 0.0;
+        __syncthreads();
+        double (*src)[kMaxB + 1] = xs;
+        if (T) {
+            double y = 0.0;
+            for (int i = 0; i <= pc; ++i) y += xs[r][i] * T[i][pc];
+            ys[r][pc] = (pc < b) ? y : 0.0;
+            __syncthreads();
+            src = ys;
+        }
+        const double mine = src[r][pc];
+#pragma unroll
+        for (int q = 0; q < kMaxB; ++q) acc[q] += mine * src[r][q];
+        __syncthreads();
+    }
+    // reduce over the 16 row-owners r in a fixed order
+#pragma unroll
+    for (int q = 0; q < kMaxB; ++q) red[(size_t)r * 256 + pc * 16 + q] = acc[q];
+    __syncthreads();
+    double v = 0.0;
+    for (int rr = 0; rr < 16; ++rr) v += red[(size_t)rr * 256 + threadIdx.x];
+    dst[(size_t)blockIdx.x * 256 + threadIdx.x] = v;
+    __syncthreads();
+}
+
+// Every block: G = sum of partials (fixed order), Cholesky R (upper), Rinv = R^-1.  Returns
+// false when a pivot is not safely positive.
+__device__ __forceinline__ bool chol_and_invert(const double *part, int b, double *G, double (*R)[kMaxB],
+                                                double (*Rinv)[kMaxB], int *s_ok, bool apply_rank_cut)
+{
+    {
+        double v = 0.0;
+        for (unsigned blk = 0; blk < gridDim.x; ++blk) v += part[(size_t)blk * 256 + threadIdx.x];
+        G[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool ok = true;
+        for (int i = 0; i < kMaxB; ++i)
+            for (int j = 0; j < kMaxB; ++j) { R[i][j] = 0.0; Rinv[i][j] = 0.0; }
+        for (int j = 0; j < b && ok; ++j) {
+            const double gjj = G[j * 16 + j];
+            double d = gjj;
+            for (int i = 0; i < j; ++i) d -= R[i][j] * R[i][j];
+            // reference rank cut: ||a_j - proj||_2 < 1e-6 (ks_utils.h:69); Gram noise floor ~ 1e-9 G_jj
+            const double floor_ = apply_rank_cut ? fmax(1e-12, 1e-9 * gjj) : 0.0;
+            if (!(d > floor_)) { ok = false; break; }
+            const double rjj = sqrt(d);
+            R[j][j] = rjj;
+            for (int c = j + 1; c < b; ++c) {
+                double t = G[j * 16 + c];
+                for (int i = 0; i < j; ++i) t -= R[i][j] * R[i][c];
+                R[j][c] = t / rjj;
+            }
+        }
+        if (ok) {   // upper-triangular inverse by back substitution, column by column
+            for (int c = 0; c < b; ++c) {
+                Rinv[c][c] = 1.0 / R[c][c];
+                for (int i = c - 1; i >= 0; --i) {
+                    double t = 0.0;
+                    for (int l = i + 1; l <= c; ++l) t += R[i][l] * Rinv[l][c];
+                    Rinv[i][c] = -t / R[i][i];
+                }
+            }
+        }
+        *s_ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+    return *s_ok != 0;
+}
+
+__global__ void __launch_bounds__(256)
+cholqr2_kernel(CholQrParams p)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double xs[16][kMaxB + 1], ys[16][kMaxB + 1];
+    __shared__ double G[256];
+    __shared__ double R1[kMaxB][kMaxB], R1i[kMaxB][kMaxB], R2[kMaxB][kMaxB], R2i[kMaxB][kMaxB], T[kMaxB][kMaxB];
+    __shared__ int s_ok;
+    extern __shared__ double red[];   // 16 x 256 doubles
+    const int b = p.b;
+    double *part0 = p.part, *part1 = p.part + (size_t)gridDim.x * 256;
+
+    gram_partial(p, nullptr, xs, ys, red, part0);
+    grid.sync();
+    if (!chol_and_invert(part0, b, G, R1, R1i, &s_ok, true)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *p.rank_out = -1;
+        return;   // uniform across the grid: every block computed the same decision
+    }
+    gram_partial(p, R1i, xs, ys, red, part1);
+    grid.sync();
+    if (!chol_and_invert(part1, b, G, R2, R2i, &s_ok, false)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *p.rank_out = -1;
+        return;
+    }
+    // T = R1^-1 R2^-1 ; R = R2 R1
+    {
+        const int i = threadIdx.x >> 4, j = threadIdx.x & 15;
+        double t = 0.0, rr = 0.0;
+        for (int l = 0; l < kMaxB; ++l) { t += R1i[i][l] * R2i[l][j]; rr += R2[i][l] * R1[l][j]; }
+        T[i][j] = t;
+        if (blockIdx.x == 0 && i < b && j < b) p.R[i + (size_t)j * b] = (float)rr;
+    }
+    __syncthreads();
+    const int pc = threadIdx.x & 15, r = threadIdx.x >> 4;
+    for (int64_t row0 = (int64_t)blockIdx.x * 16; row0 < p.n; row0 += (int64_t)gridDim.x * 16) {
+        const int64_t row = row0 + r;
+        xs[r][pc] = (row < p.n && pc < b) ? (double)p.F[row + (size_t)pc * p.n] : 0.0;
+        __syncthreads();
+        if (row < p.n && pc < b) {
+            double y = 0.0;
+            for (int i = 0; i <= pc; ++i) y += xs[r][i] * T[i][pc];
+            p.Q[row + (size_t)pc * p.n] = (float)y;
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.rank_out = b;
+}
+
+// ------------------------------------------------------------- tall-skinny panel products
+// The two block Gram-Schmidt primitives of expand() (restarted_block_ks.h:83-90) for a basis
+// W (n x rows, column-major, ld n) and a block F (n x b): HBM/L2-bound streams over W with
+// N = b <= 16, for which a library GEMM spends its time in split-K bookkeeping.
+//   wtf:   C = W^T F   per-chunk partials (fixed order -> deterministic) + ordered reduce
+//   fsub:  F -= W C,   one thread per row of F, C staged in shared memory
+static constexpr int kWtfChunk = 2048;   // rows of W per CTA
+static constexpr int kWtfCols = 32;      // columns of W per CTA (4 per warp)
+
+template <int BP>
+__global__ void __launch_bounds__(256, 2)
+wtf_partial_kernel(const float *__restrict__ W, const float *__restrict__ F, int64_t n, int rows, int b,
+                   float *__restrict__ partial /* [chunks][rows][BP] */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j0 = blockIdx.x * kWtfCols + warp * 4;
+    if (j0 >= rows) return;
+    const int64_t i0 = (int64_t)blockIdx.y * kWtfChunk;
+    float acc[4][BP];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int c = 0; c < BP; ++c) acc[jj][c] = 0.f;
+    const int nj = min(4, rows - j0);
+#pragma unroll 2
+    for (int it = 0; it < kWtfChunk / 32; ++it) {
+        const int64_t i = i0 + it * 32 + lane;
+        if (i < n) {
+            float f[BP];
+#pragma unroll
+            for (int c = 0; c < BP; ++c) f[c] = (c < b) ? F[i + (size_t)c * n] : 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                if (jj < nj) {
+                    const float w = __ldg(W + i + (size_t)(j0 + jj) * n);
+#pragma unroll
+                    for (int c = 0; c < BP; ++c) acc[jj][c] = fmaf(w, f[c], acc[jj][c]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+        for (int c = 0; c < BP; ++c) {
+            float v = acc[jj][c];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[jj][c] = v;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+            if (jj < nj) {
+#pragma unroll
+                for (int c = 0; c < BP; ++c)
+                    partial[((size_t)blockIdx.y * rows + (j0 + jj)) * BP + c] = acc[jj][c];
+            }
+    }
+}
+
+// C[j + c ldc] = sum over chunks (fixed order); optionally Hk[j + c ldh] += the same value
+template <int BP>
+__global__ void wtf_reduce_kernel(const float *__restrict__ partial, int chunks, int rows, int b,
+                                  float *__restrict__ C, int ldc, float *__restrict__ Hk, int ldh, int hk_assign)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * BP) return;
+    const int j = t / BP, c = t % BP;
+    float v = 0.f;
+    for (int ch = 0; ch < chunks; ++ch) v += partial[((size_t)ch * rows + j) * BP + c];
+    if (c < b) {
+        C[j + (size_t)c * ldc] = v;
+        if (Hk) Hk[j + (size_t)c * ldh] = hk_assign ? v : Hk[j + (size_t)c * ldh] + v;
+    }
+}
+
+template <int BP>
+__global__ void __launch_bounds__(256)
+fsub_kernel(const float *__restrict__ W, const float *__restrict__ C, int ldc, int64_t n, int rows, int b,
+            float *__restrict__ F)
+{
+    constexpr int JT = 256;
+    __shared__ __align__(16) float cs[JT][BP];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float acc[BP];
+#pragma unroll
+    for (int c = 0; c < BP; ++c) acc[c] = 0.f;
+    for (int jt = 0; jt < rows; jt += JT) {
+        const int nj = min(JT, rows - jt);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nj * BP; t += blockDim.x) {
+            const int j = t / BP, c = t % BP;
+            cs[j][c] = (c < b) ? C[(jt + j) + (size_t)c * ldc] : 0.f;
+        }
+        __syncthreads();
+        if (i < n) {
+            const float *wp = W + i + (size_t)jt * n;
+            int j = 0;
+            for (; j + 8 <= nj; j += 8) {
+                float w[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w[u] = __ldg(wp + (size_t)(j + u) * n);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                    for (int q = 0; q < BP / 4; ++q) {
+                        const float4 cv = *reinterpret_cast<const float4 *>(&cs[j + u][4 * q]);
+                        acc[4 * q] = fmaf(w[u], cv.x, acc[4 * q]);
+                        acc[4 * q + 1] = fmaf(w[u], cv.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(w[u], cv.z, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(w[u], cv.w, acc[4 * q + 3]);
+                    }
+                }
+            }
+            for (; j < nj; ++j) {
+                const float w = __ldg(wp + (size_t)j * n);
+#pragma unroll
+                for (int c = 0; c < BP; ++c) acc[c] = fmaf(w, cs[j][c], acc[c]);
+            }
+        }
+    }
+    if (i < n) {
+#pragma unroll
+        for (int c = 0; c < BP; ++c)
+            if (c < b) F[i + (size_t)c * n] -= acc[c];
+    }
+}
+
 struct KsState {
     Ctx &c;
     int64_t n;
     int k, b, ncv, m;
-    DevBuf<float> V, H, F, C, Rb, Tm, Wev, S, theta, Vtmp, Htmp, pack, work;
-    DevBuf<double> qa, qq, qpart;
+    DevBuf<float> V, H, F, C, Rb, Tm, Wev, S, theta, Vtmp, Htmp, pack, work, wpart;
+    DevBuf<double> qa, qq, qpart, cpart;
+    int chol_grid = 1, gs_passes = 3;
+    bool fast_qr = true, custom_orth = true;
     DevBuf<int> drank, dinfo;
     int lwork = 0;
     int qr_grid = 1;
@@ -269,6 +554,17 @@ struct KsState {
         int want = (int)((n + 255) / 256);
         qr_grid = std::max(1, std::min(want, c.num_sms));   // one CTA per SM at most
         qpart.alloc((size_t)2 * qr_grid * kMaxB);
+        // CholeskyQR2 fast path: as many co-resident CTAs as the 16-row tiles can use
+        ISLE_CUDA_CHECK(cudaFuncSetAttribute(cholqr2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholDynSmem));
+        ISLE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cholqr2_kernel, 256, kCholDynSmem));
+        ISLE_REQUIRE(per_sm >= 1, ISLE_ERR_CUDA, "cholqr2_kernel cannot be made resident");
+        chol_grid = std::max(1, std::min((int)((n + 15) / 16), c.num_sms * std::min(per_sm, 2)));
+        cpart.alloc((size_t)2 * chol_grid * 256);
+        const int chunks = (int)((n + kWtfChunk - 1) / kWtfChunk);
+        wpart.alloc((size_t)chunks * ncv * kMaxB);
+        fast_qr = c.opt("ks_fast_qr", 1) != 0;
+        custom_orth = c.opt("ks_custom_orth", 1) != 0;
+        gs_passes = std::max(2, std::min(3, c.opt("ks_gs_passes", 3)));
     }
 
     float *Vcol(int j) { return V.p + (size_t)j * n; }
@@ -284,14 +580,27 @@ struct KsState {
     int qr(const float *Fsrc, int cols, float *Qdst)
     {
         ISLE_CUDA_CHECK(cudaMemsetAsync(Rb.p, 0, Rb.bytes(), c.stream));
+        StatScope s(c, "ks_qr");
+        int rank = -1;
+        if (fast_qr) {
+            CholQrParams q;
+            q.F = Fsrc; q.n = n; q.b = cols; q.Q = Qdst; q.R = Rb.p; q.rank_out = drank.p; q.part = cpart.p;
+            void *qargs[] = {&q};
+            ISLE_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)cholqr2_kernel, dim3(chol_grid), dim3(256), qargs,
+                                                        kCholDynSmem, c.stream));
+            count_launch(c);
+            ISLE_CUDA_CHECK(cudaMemcpyAsync(&rank, drank.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+            ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+            if (rank >= 0) return rank;
+            c.counters["ks_qr_fallbacks"] += 1.0;
+            ISLE_CUDA_CHECK(cudaMemsetAsync(Rb.p, 0, Rb.bytes(), c.stream));
+        }
         QrParams p;
         p.F = Fsrc; p.n = n; p.b = cols; p.a = qa.p; p.q = qq.p; p.Q = Qdst; p.R = Rb.p;
         p.rank_out = drank.p; p.part = qpart.p;
         void *args[] = {&p};
-        StatScope s(c, "ks_qr");
         ISLE_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)mgs_qr64_kernel, dim3(qr_grid), dim3(256), args, 0, c.stream));
         count_launch(c);
-        int rank = 0;
         ISLE_CUDA_CHECK(cudaMemcpyAsync(&rank, drank.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
         ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
         return rank;
@@ -311,6 +620,39 @@ struct KsState {
         ISLE_CUBLAS_CHECK(cublasSgemm(c.cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, cols, rows, &mone, A, (int)n, Hm,
                                       ldh, &one, Fm, (int)n));
         count_launch(c);
+    }
+
+    // Cm(rows x b, ld ldc) = W^T Fm with W = V[:, 0:rows); when Hk != nullptr, Hk (ld ncv) is assigned
+    // (first pass) or incremented (correction passes) by the same coefficients.
+    template <int BP>
+    void wtf_t(int rows, int cols, const float *Fm, float *Cm, int ldc, float *Hk, bool assign)
+    {
+        const int chunks = (int)((n + kWtfChunk - 1) / kWtfChunk);
+        dim3 g((rows + kWtfCols - 1) / kWtfCols, chunks);
+        wtf_partial_kernel<BP><<<g, 256, 0, c.stream>>>(V.p, Fm, n, rows, cols, wpart.p);
+        wtf_reduce_kernel<BP><<<(rows * BP + 255) / 256, 256, 0, c.stream>>>(wpart.p, chunks, rows, cols, Cm, ldc, Hk,
+                                                                              ncv, assign ? 1 : 0);
+        count_launch(c, 2);
+    }
+    template <int BP>
+    void fsub_t(int rows, int cols, const float *Cm, int ldc, float *Fm)
+    {
+        fsub_kernel<BP><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(V.p, Cm, ldc, n, rows, cols, Fm);
+        count_launch(c);
+    }
+    void wtf(int rows, int cols, const float *Fm, float *Cm, int ldc, float *Hk, bool assign)
+    {
+        if (cols <= 4) wtf_t<4>(rows, cols, Fm, Cm, ldc, Hk, assign);
+        else if (cols <= 8) wtf_t<8>(rows, cols, Fm, Cm, ldc, Hk, assign);
+        else if (cols <= 12) wtf_t<12>(rows, cols, Fm, Cm, ldc, Hk, assign);
+        else wtf_t<16>(rows, cols, Fm, Cm, ldc, Hk, assign);
+    }
+    void fsub(int rows, int cols, const float *Cm, int ldc, float *Fm)
+    {
+        if (cols <= 4) fsub_t<4>(rows, cols, Cm, ldc, Fm);
+        else if (cols <= 8) fsub_t<8>(rows, cols, Cm, ldc, Fm);
+        else if (cols <= 12) fsub_t<12>(rows, cols, Cm, ldc, Fm);
+        else fsub_t<16>(rows, cols, Cm, ldc, Fm);
     }
 
     // Orthogonalised random refill of V[:, nvecs:target)  (restarted_block_ks.h:106-131, 238-258)
@@ -371,15 +713,23 @@ struct KsState {
             const int rows = H_rows, cols = H_cols;
             op(Vcol(cols), F.p);                                          // F = A V_k
             {
-                StatScope s(c, "ks_orth", 6.0 * (double)n * rows * 4.0, 12.0 * (double)n * rows * b);
+                StatScope s(c, "ks_orth", 2.0 * gs_passes * (double)n * rows * 4.0, 4.0 * gs_passes * (double)n * rows * b);
                 float *Hk = Hat(0, cols);
-                gemm_tn(rows, b, V.p, F.p, Hk, ncv);                      // Hk = W^T F
-                gemm_sub(rows, b, V.p, Hk, ncv, F.p);                     // F -= W Hk
-                for (int pass = 0; pass < 2; ++pass) {
-                    gemm_tn(rows, b, V.p, F.p, C.p, ncv);                 // Ck = W^T F
-                    gemm_sub(rows, b, V.p, C.p, ncv, F.p);                // F -= W Ck
-                    add_block_kernel<<<(rows * b + 255) / 256, 256, 0, c.stream>>>(Hk, ncv, C.p, ncv, rows, b);
-                    count_launch(c);
+                if (custom_orth) {
+                    // Hk = W^T F ; F -= W Hk ; then (gs_passes - 1) x { Ck = W^T F ; F -= W Ck ; Hk += Ck }
+                    for (int pass = 0; pass < gs_passes; ++pass) {
+                        wtf(rows, b, F.p, C.p, ncv, Hk, pass == 0);
+                        fsub(rows, b, C.p, ncv, F.p);
+                    }
+                } else {
+                    gemm_tn(rows, b, V.p, F.p, Hk, ncv);                      // Hk = W^T F
+                    gemm_sub(rows, b, V.p, Hk, ncv, F.p);                     // F -= W Hk
+                    for (int pass = 0; pass + 1 < gs_passes; ++pass) {
+                        gemm_tn(rows, b, V.p, F.p, C.p, ncv);                 // Ck = W^T F
+                        gemm_sub(rows, b, V.p, C.p, ncv, F.p);                // F -= W Ck
+                        add_block_kernel<<<(rows * b + 255) / 256, 256, 0, c.stream>>>(Hk, ncv, C.p, ncv, rows, b);
+                        count_launch(c);
+                    }
                 }
                 // new b rows of H are zero left of the R block
                 zero_block_kernel<<<(b * (cols + b) + 255) / 256, 256, 0, c.stream>>>(Hat(rows, 0), ncv, b, cols + b);
@@ -448,6 +798,8 @@ struct KsState {
         pack_residual_kernel<<<(k * b + 255) / 256, 256, 0, c.stream>>>(H.p, ncv, k, b, pack.p);
         count_launch(c);
         std::vector<float> h((size_t)(b + 1) * k);
+        // replicated ranks must take identical restart decisions: rank 0's numbers win
+        if (c.world > 1) bcast_f32(c, pack.p, h.size(), 0);
         ISLE_CUDA_CHECK(cudaMemcpyAsync(h.data(), pack.p, h.size() * 4, cudaMemcpyDeviceToHost, c.stream));
         ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
         evs.assign(h.begin(), h.begin() + k);

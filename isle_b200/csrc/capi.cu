@@ -20,6 +20,7 @@ static int guarded(isle_cuda_ctx *h, F &&f)
     if (!h) return ISLE_ERR_ARG;
     try {
         ISLE_CUDA_CHECK(cudaSetDevice(h->c.device));
+        tls_stream() = h->c.stream;
         f(h->c);
         return ISLE_OK;
     } catch (const Error &e) {
@@ -54,6 +55,12 @@ static int create_common(isle_cuda_ctx **out, int device, int rank, int world, c
     try {
         ISLE_CUDA_CHECK(cudaSetDevice(device));
         ISLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        {   // keep freed scratch memory cached in the pool instead of returning it to the driver
+            cudaMemPool_t pool;
+            ISLE_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+            uint64_t keep = UINT64_MAX;
+            ISLE_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         ISLE_CUBLAS_CHECK(cublasCreate(&c.cublas));
         ISLE_CUBLAS_CHECK(cublasSetStream(c.cublas, c.stream));
         // fp32 FMA GEMMs only: no TF32 / reduced-precision paths in the eigensolver
@@ -110,6 +117,7 @@ void isle_cuda_destroy(isle_cuda_ctx *h)
     if (!h) return;
     Ctx &c = h->c;
     cudaSetDevice(c.device);
+    tls_stream() = c.stream;
     if (c.stream) cudaStreamSynchronize(c.stream);
     for (auto &kv : c.stats)
         for (auto &ev : kv.second.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -122,7 +130,8 @@ void isle_cuda_destroy(isle_cuda_ctx *h)
     // device buffers are released by the DevBuf destructors inside Ctx
     cudaStream_t s = c.stream;
     delete h;
-    if (s) cudaStreamDestroy(s);
+    if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    tls_stream() = nullptr;
 }
 
 const char *isle_cuda_last_error(const isle_cuda_ctx *h) { return h ? h->c.last_error.c_str() : g_create_error.c_str(); }
@@ -242,6 +251,8 @@ int isle_cuda_cleanup_eigensolver(isle_cuda_ctx *h)
     return guarded(h, [&](Ctx &c) {
         c.U.release();
         c.P.release();
+        c.P_hi.release();
+        c.P_lo.release();
         c.p_l2.release();
         c.have_U = c.have_P = false;
     });

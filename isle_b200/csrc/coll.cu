@@ -32,6 +32,14 @@ void allgather_u64(Ctx &c, const unsigned long long *send, unsigned long long *r
     }
     ISLE_NCCL_CHECK(ncclAllGather(send, recv, 1, ncclUint64, c.comm, c.stream));
 }
+void allgather_f64(Ctx &c, const double *send, double *recv)
+{
+    if (c.world <= 1) {
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(recv, send, 8, cudaMemcpyDeviceToDevice, c.stream));
+        return;
+    }
+    ISLE_NCCL_CHECK(ncclAllGather(send, recv, 1, ncclFloat64, c.comm, c.stream));
+}
 void bcast_f32(Ctx &c, float *buf, size_t n, int root)
 {
     if (c.world <= 1 || n == 0) return;
@@ -48,6 +56,11 @@ void allreduce_sum_u64(Ctx &c, unsigned long long *, size_t) { need_nccl(c); }
 void allreduce_sum_f64(Ctx &c, double *, size_t) { need_nccl(c); }
 void allreduce_max_u32(Ctx &c, uint32_t *, size_t) { need_nccl(c); }
 void allgather_u64(Ctx &c, const unsigned long long *send, unsigned long long *recv)
+{
+    need_nccl(c);
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(recv, send, 8, cudaMemcpyDeviceToDevice, c.stream));
+}
+void allgather_f64(Ctx &c, const double *send, double *recv)
 {
     need_nccl(c);
     ISLE_CUDA_CHECK(cudaMemcpyAsync(recv, send, 8, cudaMemcpyDeviceToDevice, c.stream));

@@ -57,28 +57,40 @@ struct Error : public std::runtime_error {
         if (!(cond)) throw ::isle::Error((code), std::string(msg));    \
     } while (0)
 
-// Owning device buffer (cudaMalloc / cudaFree); movable, not copyable.
+// The stream device memory is allocated on / freed to: set by every C-ABI entry point to the
+// calling context's stream (one caller thread per context).  Allocation is
+// stream-ordered (cudaMallocAsync from the device's default pool with an unlimited release
+// threshold), so the per-call scratch buffers below cost no device synchronisation.
+inline cudaStream_t &tls_stream()
+{
+    static thread_local cudaStream_t s = nullptr;
+    return s;
+}
+
+// Owning device buffer (stream-ordered); movable, not copyable.
 template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    cudaStream_t s = nullptr;
     DevBuf() = default;
     explicit DevBuf(size_t n_) { alloc(n_); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
     DevBuf &operator=(DevBuf &&o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
         return *this;
     }
     ~DevBuf() { release(); }
     void alloc(size_t n_) {
         release();
         n = n_;
-        if (n) ISLE_CUDA_CHECK(cudaMalloc((void **)&p, n * sizeof(T)));
+        s = tls_stream();
+        if (n) ISLE_CUDA_CHECK(cudaMallocAsync((void **)&p, n * sizeof(T), s));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, s);
         p = nullptr;
         n = 0;
     }
@@ -129,6 +141,8 @@ struct Ctx {
     bool have_B = false;
     uint64_t DB = 0;
     int64_t nnzB = 0;
+    std::vector<uint64_t> db_all;          // D_B of every rank (doc-sharded numbering of B's columns)
+    uint64_t db_offset = 0, db_total = 0;  // first global column id of this rank; sum over ranks
     DevBuf<uint32_t> b_row;                // [nnzB] word of each nonzero, doc-major
     DevBuf<int64_t> b_off;                 // [DB+1]
     DevBuf<uint32_t> b_orig;               // [DB] original (local) doc id
@@ -145,6 +159,7 @@ struct Ctx {
     DevBuf<float> U;                       // V x k column-major
     uint64_t kp = 0;                       // padded projection width (multiple of 32)
     DevBuf<float> P;                       // DB x kp row-major, zero padded
+    DevBuf<float> P_hi, P_lo;              // split-TF32 copies of P for the tcgen05 engine (dist_tc.cu)
     DevBuf<float> p_l2;                    // DB
 
     // ---- stats / options
@@ -221,6 +236,11 @@ void lloyd_projected(Ctx &c, uint64_t k, float *centers_inout, int max_reps,
 void assign_projected(Ctx &c, uint64_t k, const float *centers, uint32_t *assign_out);
 void lift_centers(Ctx &c, uint64_t ncols, const float *in, uint64_t ld_in, float *out);
 
+// ---- dist_tc.cu (tcgen05 split-TF32 distance contraction)
+void split_tf32(Ctx &c, const float *x, size_t n, float *hi, float *lo);
+bool dist_tc_supported(const Ctx &c, uint32_t kp, uint32_t ncent);
+void dist_tc_launch(Ctx &c, const float *C, const float *c2, uint32_t ncent, int mode, uint32_t *assign, float *min_dist);
+
 // ---- collectives (no-ops when world == 1)
 void allreduce_sum_f32(Ctx &c, float *buf, size_t n);
 void allreduce_sum_u32(Ctx &c, uint32_t *buf, size_t n);
@@ -228,6 +248,7 @@ void allreduce_sum_u64(Ctx &c, unsigned long long *buf, size_t n);
 void allreduce_sum_f64(Ctx &c, double *buf, size_t n);
 void allreduce_max_u32(Ctx &c, uint32_t *buf, size_t n);
 void allgather_u64(Ctx &c, const unsigned long long *send, unsigned long long *recv);  // 1 per rank
+void allgather_f64(Ctx &c, const double *send, double *recv);                         // 1 per rank
 void bcast_f32(Ctx &c, float *buf, size_t n, int root);
 
 }  // namespace isle

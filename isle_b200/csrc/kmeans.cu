@@ -113,6 +113,15 @@ void project(Ctx &c)
             count_launch(c);
         }
     }
+    if (c.opt("dist_kernel", 1) == 1 && DB) {
+        c.P_hi.alloc((size_t)DB * kp);
+        c.P_lo.alloc((size_t)DB * kp);
+        StatScope s(c, "split_p", (double)DB * kp * 12.0);
+        split_tf32(c, c.P.p, (size_t)DB * kp, c.P_hi.p, c.P_lo.p);
+    } else {
+        c.P_hi.release();
+        c.P_lo.release();
+    }
     ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
     c.have_P = true;
 }
@@ -227,12 +236,15 @@ static void distance_pass(Ctx &c, const float *C, const float *c2, uint32_t ncen
 {
     const uint32_t DB = (uint32_t)c.DB, kp = (uint32_t)c.kp;
     if (!DB) return;
-    const bool tc = c.opt("dist_kernel", 1) == 1 && dist_tc_supported(c, kp, ncent);
+    // engine: 1 = tcgen05 split-TF32 (dist_tc.cu), 0 = SIMT fp32.  Skinny k-means++ updates (a handful of
+    // new centers) are a memory-bound pass over P and stay on the SIMT engine, which reads P once.
+    const bool tc = c.opt("dist_kernel", 1) == 1 && dist_tc_supported(c, kp, ncent) &&
+                    (mode == 0 || (int)ncent >= c.opt("dist_tc_min_centers", 32));
     // logical flops = 2 D_B ncent k
     StatScope s(c, mode == 0 ? (tc ? "dist_tc" : "dist_simt") : (tc ? "pp_dist_tc" : "pp_dist_simt"),
                 (double)DB * kp * 4.0 + (double)DB * 8.0, 2.0 * (double)DB * ncent * (double)c.k);
     if (tc) {
-        dist_tc_launch(c, c.P.p, c.p_l2.p, DB, kp, C, c2, ncent, mode, assign, min_dist);
+        dist_tc_launch(c, C, c2, ncent, mode, assign, min_dist);
         return;
     }
     const unsigned grid = (DB + 63) / 64;
@@ -408,19 +420,21 @@ struct F2D {
     __host__ __device__ double operator()(float x) const { return (double)x; }
 };
 
-// first index i with cumul[i] > t  ==  upper_bound(dist_cumul, t) - 1 of the reference (:2187)
-__global__ void upper_bound_kernel(const double *__restrict__ cumul, uint32_t n, const double *__restrict__ t,
-                                   int nt, uint32_t *__restrict__ out)
+// For each local threshold t >= 0: first index i with cumul[i] > t  ==  upper_bound(dist_cumul, t) - 1
+// of the reference (:2187); the result is the GLOBAL column id + 1 (0 = not this rank's draw).
+__global__ void pick_kernel(const double *__restrict__ cumul, uint32_t n, const double *__restrict__ t, int nt,
+                            unsigned long long offset, unsigned long long *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nt) return;
-    uint32_t lo = 0, hi = n;
     const double tv = t[i];
+    if (tv < 0.0 || n == 0) { out[i] = 0ull; return; }
+    uint32_t lo = 0, hi = n;
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
         if (cumul[mid] > tv) hi = mid; else lo = mid + 1;
     }
-    out[i] = lo < n ? lo : n - 1;
+    out[i] = offset + (lo < n ? lo : n - 1) + 1ull;
 }
 
 __global__ void fill_kernel(float *__restrict__ p, size_t n, float v)
@@ -430,64 +444,112 @@ __global__ void fill_kernel(float *__restrict__ p, size_t n, float v)
     for (; i < n; i += stride) p[i] = v;
 }
 
+// Document-sharded D^2 sampling: min_dist and its prefix sums are local to the rank
+// that owns the documents; per round the ranks exchange their partial totals (allgather of one
+// double), every rank draws the same thresholds from the same generator, the owner of each
+// threshold locates the document in its local prefix sums, and the chosen ids and then the
+// chosen rows of P travel as zero-padded allreduces.  With world == 1 the collectives vanish
+// and this is kmeanspp_on_projected_space (src/sparseMatrix.cpp:2133-2209) on one device.
 void kmeanspp(Ctx &c, uint64_t k64, uint64_t seed, uint64_t *seeds_out, float *centers_out, float *residual_out)
 {
     require_k(c, k64);
-    ISLE_REQUIRE(c.world == 1, ISLE_ERR_ARG, "kmeanspp: sharded seeding goes through kmeanspp_sharded");
     const uint32_t k = (uint32_t)k64, kp = (uint32_t)c.kp, DB = (uint32_t)c.DB;
-    ISLE_REQUIRE(DB >= k, ISLE_ERR_ARG, "kmeanspp: fewer documents than centers");   // :2137
+    const uint64_t DBtot = c.db_total;
+    ISLE_REQUIRE(DBtot >= k, ISLE_ERR_ARG, "kmeanspp: fewer documents than centers");   // :2137
+    constexpr int kMaxDraw = 64;
     std::mt19937_64 rng(seed);
     std::uniform_real_distribution<double> uni(0.0, 1.0);
-    DevBuf<float> min_dist(DB), cc((size_t)k * kp), c2(k);
-    DevBuf<double> cumul(DB), dt(64);
-    DevBuf<uint32_t> cand(64);
-    fill_kernel<<<grid_for(DB, 256), 256, 0, c.stream>>>(min_dist.p, DB, FLT_MAX);   // :2149
-    count_launch(c);
+    DevBuf<float> min_dist(std::max<uint32_t>(DB, 1)), cc((size_t)k * kp), c2(k), xch((size_t)kMaxDraw * kp);
+    DevBuf<double> cumul(std::max<uint32_t>(DB, 1)), dt(kMaxDraw), tot_mine(1), tot_all((size_t)c.world);
+    DevBuf<uint32_t> cand(kMaxDraw);
+    DevBuf<unsigned long long> gids(kMaxDraw);
+    if (DB) {
+        fill_kernel<<<grid_for(DB, 256), 256, 0, c.stream>>>(min_dist.p, DB, FLT_MAX);   // :2149
+        count_launch(c);
+    }
     size_t tb = 0;
     auto it = cub::TransformInputIterator<double, F2D, float *>(min_dist.p, F2D());
-    cub::DeviceScan::InclusiveSum(nullptr, tb, it, cumul.p, (int)DB, c.stream);
+    cub::DeviceScan::InclusiveSum(nullptr, tb, it, cumul.p, (int)std::max<uint32_t>(DB, 1), c.stream);
     DevBuf<uint8_t> tmp(tb);
 
-    std::vector<uint32_t> centers;
-    auto add_center = [&](uint32_t doc) {
-        ISLE_CUDA_CHECK(cudaMemcpyAsync(cc.p + (size_t)centers.size() * kp, c.P.p + (size_t)doc * kp, (size_t)kp * 4,
-                                        cudaMemcpyDeviceToDevice, c.stream));
-        centers.push_back(doc);
+    std::vector<uint64_t> centers;   // global column ids of B
+    auto owner_of = [&](uint64_t g) {
+        uint64_t off = 0;
+        for (int r = 0; r < c.world; ++r) { if (g < off + c.db_all[r]) return r; off += c.db_all[r]; }
+        return c.world - 1;
     };
-    add_center((uint32_t)(rng() % DB));   // :2150 picks an arbitrary first doc
+    // rows P[g] of the given global ids -> cc[centers.size() ...), on every rank
+    auto add_centers = [&](const std::vector<uint64_t> &g) {
+        if (g.empty()) return;
+        const size_t nf = g.size() * (size_t)kp;
+        if (c.world > 1) ISLE_CUDA_CHECK(cudaMemsetAsync(xch.p, 0, nf * 4, c.stream));
+        for (size_t i = 0; i < g.size(); ++i)
+            if (owner_of(g[i]) == c.rank)
+                ISLE_CUDA_CHECK(cudaMemcpyAsync(xch.p + i * kp, c.P.p + (size_t)(g[i] - c.db_offset) * kp, (size_t)kp * 4,
+                                                cudaMemcpyDeviceToDevice, c.stream));
+        if (c.world > 1) allreduce_sum_f32(c, xch.p, nf);
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(cc.p + centers.size() * (size_t)kp, xch.p, nf * 4, cudaMemcpyDeviceToDevice, c.stream));
+        centers.insert(centers.end(), g.begin(), g.end());
+    };
+    add_centers({(uint64_t)(rng() % DBtot)});   // :2150 picks an arbitrary first doc
     int new_added = 1;
     double total = 0.0;
+    std::vector<double> totals((size_t)c.world), prefix((size_t)c.world + 1);
     while (centers.size() < k) {
         StatScope s(c, "pp_round");
         const uint32_t first = (uint32_t)centers.size() - new_added;
         row_l2_kernel<<<(new_added * 32 + 255) / 256, 256, 0, c.stream>>>(cc.p + (size_t)first * kp, new_added, kp, c2.p + first);
         count_launch(c);
         distance_pass(c, cc.p + (size_t)first * kp, c2.p + first, (uint32_t)new_added, 1, nullptr, min_dist.p);
-        ISLE_CUDA_CHECK(cub::DeviceScan::InclusiveSum(tmp.p, tb, it, cumul.p, (int)DB, c.stream));
-        count_launch(c);
-        ISLE_CUDA_CHECK(cudaMemcpyAsync(&total, cumul.p + (DB - 1), 8, cudaMemcpyDeviceToHost, c.stream));
+        if (DB) {
+            ISLE_CUDA_CHECK(cub::DeviceScan::InclusiveSum(tmp.p, tb, it, cumul.p, (int)DB, c.stream));
+            count_launch(c);
+            ISLE_CUDA_CHECK(cudaMemcpyAsync(tot_mine.p, cumul.p + (DB - 1), 8, cudaMemcpyDeviceToDevice, c.stream));
+        } else {
+            ISLE_CUDA_CHECK(cudaMemsetAsync(tot_mine.p, 0, 8, c.stream));
+        }
+        allgather_f64(c, tot_mine.p, tot_all.p);
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(totals.data(), tot_all.p, totals.size() * 8, cudaMemcpyDeviceToHost, c.stream));
         ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        prefix[0] = 0.0;
+        for (int r = 0; r < c.world; ++r) prefix[r + 1] = prefix[r] + totals[r];
+        total = prefix[c.world];
         // draw 1 + sqrt(max(s-5,0)) candidates (:2181-2199); duplicates are skipped
         const int s_now = (int)centers.size();
-        int ndraw = 0;
         std::vector<double> ts;
-        for (int d = 0; d < 1 + std::sqrt((double)(s_now - 5 > 0 ? s_now - 5 : 0)); ++d) { ts.push_back(total * uni(rng)); ++ndraw; }
-        ndraw = std::min(ndraw, 64);
-        ISLE_CUDA_CHECK(cudaMemcpyAsync(dt.p, ts.data(), (size_t)ndraw * 8, cudaMemcpyHostToDevice, c.stream));
-        upper_bound_kernel<<<1, 64, 0, c.stream>>>(cumul.p, DB, dt.p, ndraw, cand.p);
+        for (int d = 0; d < 1 + std::sqrt((double)(s_now - 5 > 0 ? s_now - 5 : 0)) && (int)ts.size() < kMaxDraw; ++d)
+            ts.push_back(total * uni(rng));
+        const int ndraw = (int)ts.size();
+        // thresholds that fall into this rank's share of the prefix sums, made local
+        std::vector<double> tl(ndraw, -1.0);
+        for (int d = 0; d < ndraw; ++d) {
+            int r = 0;
+            while (r + 1 < c.world && ts[d] >= prefix[r + 1]) ++r;
+            while (r > 0 && totals[r] <= 0.0) --r;           // never hand a draw to an empty shard
+            if (r == c.rank && DB) tl[d] = std::max(0.0, ts[d] - prefix[r]);
+        }
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(dt.p, tl.data(), (size_t)ndraw * 8, cudaMemcpyHostToDevice, c.stream));
+        pick_kernel<<<1, kMaxDraw, 0, c.stream>>>(cumul.p, DB, dt.p, ndraw, c.db_offset, gids.p);
         count_launch(c);
-        std::vector<uint32_t> hc(ndraw);
-        ISLE_CUDA_CHECK(cudaMemcpyAsync(hc.data(), cand.p, (size_t)ndraw * 4, cudaMemcpyDeviceToHost, c.stream));
+        if (c.world > 1) allreduce_sum_u64(c, gids.p, (size_t)ndraw);
+        std::vector<unsigned long long> hg(ndraw);
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(hg.data(), gids.p, (size_t)ndraw * 8, cudaMemcpyDeviceToHost, c.stream));
         ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-        new_added = 0;
-        for (int d = 0; d < ndraw && centers.size() < k; ++d) {
-            if (std::find(centers.begin(), centers.end(), hc[d]) == centers.end()) { add_center(hc[d]); ++new_added; }
+        std::vector<uint64_t> fresh;
+        for (int d = 0; d < ndraw && centers.size() + fresh.size() < k; ++d) {
+            if (hg[d] == 0) continue;                       // no owner (total == 0)
+            const uint64_t g = hg[d] - 1;
+            if (std::find(centers.begin(), centers.end(), g) == centers.end() &&
+                std::find(fresh.begin(), fresh.end(), g) == fresh.end())
+                fresh.push_back(g);
         }
-        if (new_added == 0 && total <= 0.0) {
+        if (fresh.empty() && total <= 0.0) {
             // degenerate corpus (all remaining docs coincide with a center): fall back to unused docs
-            for (uint32_t d = 0; d < DB && centers.size() < k; ++d)
-                if (std::find(centers.begin(), centers.end(), d) == centers.end()) { add_center(d); ++new_added; }
+            for (uint64_t g = 0; g < DBtot && centers.size() + fresh.size() < k && fresh.size() < (size_t)kMaxDraw; ++g)
+                if (std::find(centers.begin(), centers.end(), g) == centers.end()) fresh.push_back(g);
         }
+        add_centers(fresh);
+        new_added = (int)fresh.size();
     }
     if (seeds_out) for (uint32_t i = 0; i < k; ++i) seeds_out[i] = centers[i];
     if (centers_out)   // kmeans_init_on_projected_space copies U^T doc for each seed (:2232-2234)

@@ -341,6 +341,22 @@ void build_B(Ctx &c, const uint8_t *select, int64_t *nnzB_out, uint64_t *DB_out)
         ISLE_CUDA_CHECK(cudaMemcpyAsync(c.b_off.p + DB, &c.nnzB, 8, cudaMemcpyHostToDevice, c.stream));
     }
     ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    {   // global numbering of B's columns: rank r owns [db_offset, db_offset + D_B)  
+        c.db_all.assign((size_t)c.world, 0);
+        DevBuf<unsigned long long> mine(1), all((size_t)c.world);
+        unsigned long long v = DB;
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(mine.p, &v, 8, cudaMemcpyHostToDevice, c.stream));
+        allgather_u64(c, mine.p, all.p);
+        std::vector<unsigned long long> h((size_t)c.world);
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(h.data(), all.p, h.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        c.db_offset = c.db_total = 0;
+        for (int r = 0; r < c.world; ++r) {
+            c.db_all[r] = h[r];
+            if (r < c.rank) c.db_offset += h[r];
+            c.db_total += h[r];
+        }
+    }
     c.have_B = true;
     c.have_csr = c.have_U = c.have_P = false;
     if (nnzB_out) *nnzB_out = nnzB;
