@@ -1,0 +1,269 @@
+// sparseMatrix_cuda.cpp -- the reference-side binding of libisle_cuda.
+//
+// This translation unit is compiled WITH the reference's own headers (include/sparseMatrix.h)
+// and linked into ISLETrain next to the reference's unmodified objects.  It supplies, as
+// explicit specialisations for FPTYPE = float, exactly the member functions that
+// ISLETrainer::train() calls on the spectral core (reference src/trainer.cpp:430-554); each one
+// forwards to the C ABI in include/isle_cuda.h.  Explicit specialisations are ordinary (strong)
+// symbols, while the reference's `template class ISLE::FPSparseMatrix<float>;`
+// (src/sparseMatrix.cpp:2495-2510) emits weak ones, so the linker binds trainer.o to the
+// functions below and everything else (run_lloyds on full B, catchwords, topic model, output
+// writers) keeps running the reference's host code on the arrays this file fills.
+//
+//   reference member (include/sparseMatrix.h)            line   C ABI entry point
+//   SparseMatrix::list_word_freqs_by_sorting              :116   (no-op: freqs is only a hand-off)
+//   SparseMatrix::compute_thresholds                      :128   isle_cuda_upload_A + isle_cuda_thresholds
+//   FPSparseMatrix::threshold_and_copy<float>             :278   isle_cuda_build_B + isle_cuda_download_B
+//   FPSparseMatrix::sampled_threshold_and_copy<float>     :297   isle_cuda_sampling_weights + build_B(mask)
+//   FPSparseMatrix::frobenius                             :242   isle_cuda_frobenius
+//   FPSparseMatrix::initialize_for_eigensolver            :258   (allocates U_colmajor as the reference does)
+//   FPSparseMatrix::compute_block_ks                      :266   isle_cuda_block_ks
+//   FPSparseMatrix::kmeans_init_on_projected_space        :454   isle_cuda_kmeanspp
+//   FPSparseMatrix::run_lloyds_on_projected_space         :434   isle_cuda_lloyd_projected
+//   FPSparseMatrix::left_multiply_by_U_Spectra            :309   isle_cuda_lift_centers
+//   FPSparseMatrix::cleanup_after_eigensolver             :260   isle_cuda_cleanup_eigensolver
+//
+// Ownership follows the reference: every host array is new[]-allocated here to the size the
+// reference would have used and filled by the library; device memory belongs to the context.
+// Errors become std::runtime_error, which main()'s catch-all reports as "ISLE Trainer failed"
+// (drivers/ISLETrain.cpp:48-50).  train() is single-threaded, so one process-wide context.
+#include <algorithm>
+#include <cstdlib>
+#include <functional>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "sparseMatrix.h"
+
+#include "isle_cuda.h"
+
+namespace {
+
+isle_cuda_ctx *g_ctx = nullptr;
+
+isle_cuda_ctx *ctx()
+{
+    if (!g_ctx) {
+        const char *dev = std::getenv("ISLE_CUDA_DEVICE");
+        const int rc = isle_cuda_create(&g_ctx, dev ? std::atoi(dev) : 0);
+        if (rc != ISLE_OK)
+            throw std::runtime_error(std::string("libisle_cuda: ") + isle_cuda_last_error(nullptr));
+    }
+    return g_ctx;
+}
+
+void check(int rc, const char *what)
+{
+    if (rc != ISLE_OK)
+        throw std::runtime_error(std::string("libisle_cuda: ") + what + ": " + isle_cuda_last_error(g_ctx));
+}
+
+}  // namespace
+
+namespace ISLE
+{
+    // ---- stage A ----------------------------------------------------------------------------
+    template<>
+    void SparseMatrix<float>::list_word_freqs_by_sorting(std::vector<A_TYPE>*)
+    {
+        // The device path selects thresholds from per-word histograms of the rounded values;
+        // the word-major lists the reference builds here are never needed.
+    }
+
+    template<>
+    offset_t SparseMatrix<float>::compute_thresholds(
+        word_id_t word_begin,
+        word_id_t word_end,
+        std::vector<A_TYPE> *const,
+        std::vector<float>& zetas,
+        const doc_id_t num_topics)
+    {
+        if (word_begin != 0 || word_end != vocab_size())
+            throw std::runtime_error("libisle_cuda: thresholds are computed for the whole vocabulary at once");
+        check(isle_cuda_upload_A(ctx(), vocab_size(), num_docs(), get_nnzs(), normalized_vals_CSC,
+                                 (const uint64_t *)rows_CSC, (const int64_t *)offsets_CSC,
+                                 (float)avg_doc_sz, (uint64_t)_nz_docs), "upload_A");
+        zetas.resize(vocab_size());
+        int64_t new_nnzs = 0;
+        check(isle_cuda_thresholds(ctx(), num_topics, zetas.data(), &new_nnzs), "thresholds");
+        return (offset_t)new_nnzs;
+    }
+
+    // ---- stage B ----------------------------------------------------------------------------
+    namespace {
+        void build_and_download(FPSparseMatrix<float>& B, const uint8_t *mask, const offset_t nnzs,
+                                std::vector<doc_id_t>& original_cols,
+                                float *&vals, word_id_t *&rows, offset_t *&offsets,
+                                offset_t &nnzs_out, doc_id_t &docs_out)
+        {
+            int64_t nnzB = 0;
+            uint64_t DB = 0;
+            check(isle_cuda_build_B(ctx(), mask, &nnzB, &DB), "build_B");
+            if (nnzB > nnzs + 1000)     // the reference allocates nnzs + 1000 (src/sparseMatrix.cpp:1295-1296)
+                throw std::runtime_error("libisle_cuda: B holds more entries than compute_thresholds announced");
+            original_cols.resize(DB);
+            static_assert(sizeof(doc_id_t) == sizeof(uint64_t) && sizeof(offset_t) == sizeof(int64_t),
+                          "the C ABI assumes the reference's ILP64 index types");
+            check(isle_cuda_download_B(ctx(), vals, (uint64_t *)rows, (int64_t *)offsets,
+                                       (uint64_t *)original_cols.data()), "download_B");
+            nnzs_out = (offset_t)nnzB;
+            docs_out = (doc_id_t)DB;
+            (void)B;
+        }
+    }
+
+    template<>
+    template<>
+    void FPSparseMatrix<float>::threshold_and_copy<float>(
+        const SparseMatrix<float>& from,
+        const std::vector<float>& zetas,
+        const offset_t nnzs,
+        std::vector<doc_id_t>& original_cols)
+    {
+        assert(vocab_size() == from.vocab_size() && num_docs() == from.num_docs());
+        assert(original_cols.size() == 0); assert(zetas.size() == vocab_size());
+        allocate(nnzs + 1000);                                  // src/sparseMatrix.cpp:1295-1296
+        offset_t n = 0; doc_id_t d = 0;
+        build_and_download(*this, nullptr, nnzs, original_cols, vals_CSC, rows_CSC, offsets_CSC, n, d);
+        _num_docs = d;                                          // :1309
+        std::cout << "Columns remaining after thresholding: " << d << "\n";
+        _nnzs = n;                                              // :1320
+    }
+
+    template<>
+    template<>
+    void FPSparseMatrix<float>::sampled_threshold_and_copy<float>(
+        const SparseMatrix<float>& from,
+        const std::vector<float>& zetas,
+        const offset_t nnzs,
+        std::vector<doc_id_t>& original_cols,
+        const float sample_rate)
+    {
+        assert(vocab_size() == from.vocab_size() && num_docs() == from.num_docs());
+        assert(original_cols.size() == 0); assert(zetas.size() == vocab_size());
+        allocate(nnzs + 1000);
+        // weights on the device (:1383-1397); keys, pivot and selection exactly as :1399-1415,
+        // but with the rand() draws taken serially (the reference races on rand() under pfor)
+        const doc_id_t D = from.num_docs();
+        std::vector<float> weights(D), dice(D);
+        check(isle_cuda_sampling_weights(ctx(), weights.data()), "sampling_weights");
+        for (doc_id_t doc = 0; doc < D; ++doc) {
+            dice[doc] = weights[doc] == 0.0f ? 0.0f : (float)std::pow(rand_fraction(), 1 / weights[doc]);
+            weights[doc] = dice[doc];
+        }
+        const size_t nth = (size_t)(sample_rate * (float)D);
+        std::nth_element(dice.begin(), dice.begin() + nth, dice.end(), std::greater<float>());
+        const float pivot = dice[nth];
+        std::cout << "sampling docs: pivot: " << pivot << std::endl;
+        std::vector<uint8_t> select(D);
+        for (doc_id_t doc = 0; doc < D; ++doc) select[doc] = weights[doc] >= pivot;
+        offset_t n = 0; doc_id_t d = 0;
+        build_and_download(*this, select.data(), nnzs, original_cols, vals_CSC, rows_CSC, offsets_CSC, n, d);
+        _num_docs = d;
+        std::cout << "After sampling docs: cols remaining: " << d << "\n";
+        _nnzs = n;
+        this->shrink(n);                                        // :1428
+    }
+
+    template<>
+    float FPSparseMatrix<float>::frobenius() const
+    {
+        float f = 0.0f;
+        check(isle_cuda_frobenius(ctx(), &f), "frobenius");
+        return f;
+    }
+
+    // ---- stage C ----------------------------------------------------------------------------
+    template<>
+    void FPSparseMatrix<float>::initialize_for_eigensolver(const doc_id_t num_topics)
+    {
+        U_rows = vocab_size();
+        U_cols = num_topics;
+        U_colmajor = new float[(size_t)num_topics * (size_t)vocab_size()];   // :1154
+    }
+
+    template<>
+    void FPSparseMatrix<float>::compute_block_ks(
+        const doc_id_t num_topics,
+        std::vector<float>& evalues)
+    {
+        std::vector<float> ev(num_topics);
+        int nconv = 0;
+        const int rc = isle_cuda_block_ks(ctx(), num_topics, BLOCK_KS_BLOCK_SIZE, BLOCK_KS_MAX_ITERS,
+                                          (float)BLOCK_KS_TOLERANCE, /*seed=*/0, ev.data(), U_colmajor, &nconv);
+        // the reference asserts num_converged() == num_topics (:1207)
+        check(rc, "block_ks");
+        for (doc_id_t i = 0; i < num_topics; ++i) evalues.push_back(ev[i]);
+        // U_rowmajor only feeds the host projection path this library replaces; stages F-H never
+        // read it, so it is left unallocated (the destructor handles NULL).
+    }
+
+    template<>
+    void FPSparseMatrix<float>::cleanup_after_eigensolver()
+    {
+        assert(U_colmajor != NULL);
+        delete[] U_colmajor;
+        U_colmajor = NULL;
+        check(isle_cuda_cleanup_eigensolver(ctx()), "cleanup_eigensolver");
+    }
+
+    // ---- stages D / E -----------------------------------------------------------------------
+    template<>
+    float FPSparseMatrix<float>::kmeans_init_on_projected_space(
+        const int num_centers,
+        const int max_reps,
+        std::vector<doc_id_t>& best_seed,
+        float *const best_centers_coords)
+    {
+        float best = FP_MAX;
+        std::vector<uint64_t> seeds(num_centers);
+        std::vector<float> coords((size_t)num_centers * num_centers);
+        for (int rep = 0; rep < max_reps; ++rep) {
+            float dist = 0.0f;
+            check(isle_cuda_kmeanspp(ctx(), num_centers, (uint64_t)rep, seeds.data(), coords.data(), &dist), "kmeanspp");
+            std::cout << "k-means init residual: " << dist << std::endl;
+            if (dist < best) {
+                best = dist;
+                best_seed.assign(seeds.begin(), seeds.end());
+                if (best_centers_coords)
+                    std::copy(coords.begin(), coords.end(), best_centers_coords);
+            }
+        }
+        return best;
+    }
+
+    template<>
+    float FPSparseMatrix<float>::run_lloyds_on_projected_space(
+        const doc_id_t num_centers,
+        float *projected_centers,
+        std::vector<doc_id_t> *closest_docs,
+        const int max_reps)
+    {
+        std::vector<uint32_t> assign;
+        if (closest_docs != NULL) {
+            for (doc_id_t center = 0; center < num_centers; ++center)
+                assert(closest_docs[center].size() == 0);
+            assign.resize(num_docs());
+        }
+        check(isle_cuda_lloyd_projected(ctx(), num_centers, projected_centers, max_reps,
+                                        closest_docs ? assign.data() : NULL, NULL, NULL), "lloyd_projected");
+        if (closest_docs != NULL)
+            for (doc_id_t d = 0; d < num_docs(); ++d)
+                closest_docs[assign[d]].push_back(d);            // ascending doc ids, as :1966-1973
+        return 0.0f;                                             // the reference's residual is always 0
+    }
+
+    template<>
+    void FPSparseMatrix<float>::left_multiply_by_U_Spectra(
+        float *const out,
+        const float *in,
+        const doc_id_t ld_in,
+        const doc_id_t ncols)
+    {
+        assert(U_rows == (MKL_INT)vocab_size());
+        assert(ld_in >= (doc_id_t)U_cols);
+        check(isle_cuda_lift_centers(ctx(), ncols, in, ld_in, out), "lift_centers");
+    }
+}
