@@ -58,8 +58,11 @@ def parse():
 
 # ------------------------------------------------------------------------------- helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler process is
+    started before the warm-up (its start-up initialises NVML on every GPU of the box, which stalls
+    CUDA calls of running processes for ~100 ms when other GPUs are idle); mark()/stop() keep only the
+    samples whose timestamps fall inside the timed region."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -67,18 +70,26 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(prefix="isle_clocks_", suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self) -> dict:
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.proc:
             return out
@@ -88,19 +99,29 @@ class ClockSampler:
         except Exception:
             pass
         try:
-            sm, mx, reasons = [], [], set()
+            sm, mx, reasons, all_sm, all_mx = [], [], set(), [], []
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
+                if len(f) < 10:
                     continue
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                try:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except Exception:
+                    ts = None
+                all_sm.append(float(f[2])); all_mx.append(float(f[3]))
+                if ts is None or self.t0 is None or not (self.t0 - 0.05 <= ts <= self.t1 + 0.05):
+                    continue
+                sm.append(float(f[2])); mx.append(float(f[3]))
                 for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                     f[5:9]):
+                                     f[6:10]):
                     if val.lower().startswith("active"):
                         reasons.add(name)
             if sm:
                 out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
                        "samples": len(sm)}
+            elif all_sm:   # timed region shorter than the sampling period: nearest samples of the run
+                out = {"sm_mhz": float(np.median(all_sm[-5:])), "sm_max_mhz": float(max(all_mx)), "reasons": [],
+                       "samples": 0, "note": "no sample fell inside the timed region; last samples of the run"}
             os.unlink(self.path)
         except Exception:
             pass
@@ -145,7 +166,9 @@ def make_corpus(name, rank, seed):
     from isle_b200 import corpus
     cfg = dict(corpus.CONFIGS[name])
     backend = "torch" if (torch.cuda.is_available() and cfg["D"] * 50 > 2_000_000) else "numpy"
-    return corpus.generate(V=cfg["V"], D=cfg["D"], k=cfg["k"], mu=cfg["mu"], seed=cfg["seed"] + 1000 * rank + seed,
+    # every rank draws its own documents from the SAME topic model (one corpus, sharded by documents)
+    return corpus.generate(V=cfg["V"], D=cfg["D"], k=cfg["k"], mu=cfg["mu"], seed=cfg["seed"] + seed,
+                           doc_seed=rank if rank else None,
                            backend=backend, device=f"cuda:{torch.cuda.current_device()}" if backend == "torch" else "cpu")
 
 
@@ -197,9 +220,8 @@ def bench_ours(args):
     import torch
     import torch.distributed as dist
 
-    from isle_b200 import _capi, corpus
+    from isle_b200 import _capi, corpus, sharding
     from isle_b200._capi import ptr
-    from oracle import isle_oracle as O   # cpu_baseline leg + input normalisation only
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -220,18 +242,10 @@ def bench_ours(args):
     V, k = cfg["V"], cfg["k"]
     c = make_corpus(args.config, rank, args.seed)
     D, nnz = c.D, c.nnz
-    # input normalisation = ISLETrainer's own ingest (populate_CSC + normalize_docs), outside the path
-    if world > 1:
-        tot = torch.tensor([int(c.counts.astype(np.uint64).sum()), int((np.diff(c.offsets) > 0).sum())],
-                           dtype=torch.int64, device="cuda")
-        dist.all_reduce(tot)
-        avg = np.float32(int(tot[0].item()) // int(tot[1].item()))
-        lens = np.diff(c.offsets)
-        sums = np.add.reduceat(c.counts.astype(np.int64), c.offsets[:-1])
-        vals = (avg * (c.counts.astype(np.float32) / np.repeat(sums.astype(np.float32), lens))).astype(np.float32)
-        nz_local = int((lens > 0).sum())
-    else:
-        vals, avg, nz_local = O.normalize_docs(c.counts, c.offsets)
+    # input normalisation = ISLETrainer's own ingest (populate_CSC + normalize_docs), outside the path;
+    # avg_doc_sz is a statistic of the whole corpus, so shards exchange token / document totals
+    avg, nz_local, _nz_global = sharding.global_doc_stats(c.counts, c.offsets)
+    vals = sharding.normalize_shard(c.counts, c.offsets, avg)
     h_vals = pinned(vals)
     h_rows64 = pinned(c.rows.astype(np.uint64))
     h_offs = pinned(c.offsets.astype(np.int64))
@@ -268,6 +282,8 @@ def bench_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     # ---- warm-up: full end-to-end steps
     for i in range(args.warmup):
         upload()
@@ -277,16 +293,18 @@ def bench_ours(args):
     upload()
     ctx.call("isle_cuda_reset_stats")
     ctx.call("isle_cuda_set_profiling", 1)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     ctx.call("isle_cuda_timer_start")
+    step_wall = []
     for i in range(args.steps):
+        tw = time.perf_counter()
         core(False, args.seed + 100 + i)
+        step_wall.append((time.perf_counter() - tw) * 1e3)
     ms = C.c_double()
     ctx.call("isle_cuda_timer_stop", C.byref(ms))
     barrier()
-    clocks = sampler.stop()
+    sampler.mark_end()
     dev_ms = ms.value
     st = {n: ctx.stat(n) for n in ("launches", "spmm_bt_ms", "spmm_bt_bytes", "spmm_bt_calls", "spmm_b_ms",
                                    "spmm_b_bytes", "spmm_b_calls", "ks_op_ms", "ks_orth_ms", "ks_qr_ms",
@@ -303,6 +321,7 @@ def bench_ours(args):
         core(True, args.seed + 200 + i)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
 
     if world > 1:
         tt = torch.tensor([dev_ms, e2e_s, float(D)], dtype=torch.float64, device="cuda")
@@ -340,6 +359,7 @@ def bench_ours(args):
                          "avg_launch_ms": spmm_ms / ncalls if ncalls else None,
                          "bytes_per_launch": spmm_bytes / ncalls if ncalls else None},
             "stage_ms_per_step": {n[:-3]: st[n] / args.steps for n in st if n.endswith("_ms")},
+            "step_wall_ms": [round(x, 2) for x in step_wall],
         }
         if not args.no_cpu_baseline and world == 1:
             try:

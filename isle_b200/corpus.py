@@ -87,14 +87,18 @@ def _topics(V: int, k: int, rng: np.random.Generator) -> np.ndarray:
 
 
 def generate(name: str | None = None, *, V: int = 0, D: int = 0, k: int = 0, mu: float = 4.5,
-             seed: int = 0, backend: str = "numpy", device: str = "cuda") -> Corpus:
+             seed: int = 0, backend: str = "numpy", device: str = "cuda", doc_seed: int | None = None) -> Corpus:
+    """``seed`` fixes the topic model; ``doc_seed`` (default: continue the same stream) draws a
+    different set of documents from it -- document shards of one corpus for the multi-GPU runs."""
     if name is not None:
         cfg = dict(CONFIGS[name])
         V, D, k, mu, seed = cfg["V"], cfg["D"], cfg["k"], cfg["mu"], cfg["seed"]
     if backend == "torch":
-        return _generate_torch(V, D, k, mu, seed, device)
+        return _generate_torch(V, D, k, mu, seed, device, doc_seed)
     rng = np.random.Generator(np.random.PCG64(seed))
     T = _topics(V, k, rng)
+    if doc_seed is not None:
+        rng = np.random.Generator(np.random.PCG64([seed, doc_seed]))
     cdf = np.cumsum(T, axis=1)
     cdf /= cdf[:, -1:]
     flat = (cdf + np.arange(k)[:, None]).ravel()  # monotone over (topic, word)
@@ -138,7 +142,7 @@ def _rowwise_search(mcdf: np.ndarray, tok_doc: np.ndarray, u: np.ndarray) -> np.
     return np.searchsorted(flat, tok_doc + u, side="right") - tok_doc * k
 
 
-def _generate_torch(V: int, D: int, k: int, mu: float, seed: int, device: str) -> Corpus:
+def _generate_torch(V: int, D: int, k: int, mu: float, seed: int, device: str, doc_seed: int | None = None) -> Corpus:
     """Same model drawn with torch on ``device`` (bench-sized corpora in seconds)."""
     import torch
 
@@ -166,6 +170,8 @@ def _generate_torch(V: int, D: int, k: int, mu: float, seed: int, device: str) -
         del noise, T, c
     flat = torch.cat(flat_parts)
     del flat_parts
+    if doc_seed is not None:
+        g.manual_seed(seed * 1000003 + doc_seed + 1)
 
     dominant = torch.randint(0, k, (D,), generator=g, device=dev)
     L = torch.empty(D, dtype=torch.float64, device=dev).normal_(mu, 0.5, generator=g).exp_()

@@ -258,9 +258,15 @@ __device__ __forceinline__ void gram_partial(const CholQrParams &p, const double
     double acc[kMaxB];
 #pragma unroll
     for (int q = 0; q < kMaxB; ++q) acc[q] = 0.0;
-    for (int64_t row0 = (int64_t)blockIdx.x * 16; row0 < p.n; row0 += (int64_t)gridDim.x * 16) {
-        const int64_t row = row0 + r;
-        xs[r][pc] = (row < p.n && pc < b) ? (double)p.F[row + (size_t)pc * p.n] : 0.0;
+    const int64_t step = (int64_t)gridDim.x * 16;
+    int64_t row0 = (int64_t)blockIdx.x * 16;
+    float nxt = (row0 + r < p.n && pc < b) ? p.F[row0 + r + (size_t)pc * p.n] : 0.f;
+    for (; row0 < p.n; row0 += step) {
+        xs[r][pc] = (double)nxt;
+        {   // prefetch the next tile's element while this one is reduced
+            const int64_t rown = row0 + step + r;
+            nxt = (rown < p.n && pc < b) ? p.F[rown + (size_t)pc * p.n] : 0.f;
+        }
         __syncthreads();
         double (*src)[kMaxB + 1] = xs;
         if (T) {
@@ -385,7 +391,7 @@ cholqr2_kernel(CholQrParams p)
 // N = b <= 16, for which a library GEMM spends its time in split-K bookkeeping.
 //   wtf:   C = W^T F   per-chunk partials (fixed order -> deterministic) + ordered reduce
 //   fsub:  F -= W C,   one thread per row of F, C staged in shared memory
-static constexpr int kWtfChunk = 2048;   // rows of W per CTA
+static constexpr int kWtfChunk = 512;    // rows of W per CTA
 static constexpr int kWtfCols = 32;      // columns of W per CTA (4 per warp)
 
 template <int BP>
@@ -403,21 +409,20 @@ wtf_partial_kernel(const float *__restrict__ W, const float *__restrict__ F, int
 #pragma unroll
         for (int c = 0; c < BP; ++c) acc[jj][c] = 0.f;
     const int nj = min(4, rows - j0);
-#pragma unroll 2
+    // all loads of an iteration are issued before the first FMA; 16 iterations per CTA
+#pragma unroll 1
     for (int it = 0; it < kWtfChunk / 32; ++it) {
         const int64_t i = i0 + it * 32 + lane;
         if (i < n) {
-            float f[BP];
+            float f[BP], w[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) w[jj] = (jj < nj) ? __ldg(W + i + (size_t)(j0 + jj) * n) : 0.f;
 #pragma unroll
             for (int c = 0; c < BP; ++c) f[c] = (c < b) ? F[i + (size_t)c * n] : 0.f;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                if (jj < nj) {
-                    const float w = __ldg(W + i + (size_t)(j0 + jj) * n);
+            for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-                    for (int c = 0; c < BP; ++c) acc[jj][c] = fmaf(w, f[c], acc[jj][c]);
-                }
-            }
+                for (int c = 0; c < BP; ++c) acc[jj][c] = fmaf(w[jj], f[c], acc[jj][c]);
         }
     }
 #pragma unroll
@@ -558,7 +563,7 @@ struct KsState {
         ISLE_CUDA_CHECK(cudaFuncSetAttribute(cholqr2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholDynSmem));
         ISLE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cholqr2_kernel, 256, kCholDynSmem));
         ISLE_REQUIRE(per_sm >= 1, ISLE_ERR_CUDA, "cholqr2_kernel cannot be made resident");
-        chol_grid = std::max(1, std::min((int)((n + 15) / 16), c.num_sms * std::min(per_sm, 2)));
+        chol_grid = std::max(1, std::min((int)((n + 15) / 16), c.num_sms * std::min(per_sm, 4)));
         cpart.alloc((size_t)2 * chol_grid * 256);
         const int chunks = (int)((n + kWtfChunk - 1) / kWtfChunk);
         wpart.alloc((size_t)chunks * ncv * kMaxB);

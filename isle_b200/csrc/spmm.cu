@@ -166,7 +166,20 @@ void build_csr(Ctx &c)
 // Per step each lane loads one index (coalesced 16 B per group), indices are exchanged by
 // shuffle and four independent float4 gathers are issued before they are summed, in a fixed
 // order so that results are run-to-run deterministic for unsplit rows.
-template <int NCH>
+// Index stream loads: read once, so optionally kept out of L1 (ld.global.nc.L1::no_allocate) to leave
+// the cache to the gathered dense rows.
+template <bool NOALLOC>
+__device__ __forceinline__ uint32_t ld_idx(const uint32_t *p)
+{
+    if (NOALLOC) {
+        uint32_t v;
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+        return v;
+    }
+    return __ldg(p);
+}
+
+template <int NCH, bool NOALLOC>
 __global__ void __launch_bounds__(256)
 spmm_gather_kernel(const WorkItem *__restrict__ items, size_t n_items, const uint32_t *__restrict__ idx,
                    const float4 *__restrict__ in, float4 *__restrict__ out)
@@ -182,7 +195,7 @@ spmm_gather_kernel(const WorkItem *__restrict__ items, size_t n_items, const uin
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t j = 0;
     for (; j + 8 <= len; j += 8) {
-        const uint32_t i0 = p[j + sub], i1 = p[j + 4 + sub];
+        const uint32_t i0 = ld_idx<NOALLOC>(p + j + sub), i1 = ld_idx<NOALLOC>(p + j + 4 + sub);
         float4 v[8];
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
@@ -199,7 +212,7 @@ spmm_gather_kernel(const WorkItem *__restrict__ items, size_t n_items, const uin
         }
     }
     for (; j < len; j += 4) {
-        const uint32_t i0 = (j + sub < len) ? p[j + sub] : 0u;
+        const uint32_t i0 = (j + sub < len) ? ld_idx<NOALLOC>(p + j + sub) : 0u;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             const uint32_t r0 = __shfl_sync(gmask, i0, s, 4);
@@ -258,12 +271,19 @@ static void launch_gather(Ctx &c, int nch, const WorkItem *items, size_t n_items
     const unsigned grid = (unsigned)((n_items * 4 + 255) / 256);
     const float4 *in4 = reinterpret_cast<const float4 *>(in);
     float4 *out4 = reinterpret_cast<float4 *>(out);
+    const bool na = c.opt("spmm_idx_noalloc", 1) != 0;
+#define ISLE_SPMM_LAUNCH(N)                                                                                    \
+    do {                                                                                                       \
+        if (na) spmm_gather_kernel<N, true><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in4, out4);       \
+        else spmm_gather_kernel<N, false><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in4, out4);         \
+    } while (0)
     switch (nch) {
-    case 1: spmm_gather_kernel<1><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in4, out4); break;
-    case 2: spmm_gather_kernel<2><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in4, out4); break;
-    case 3: spmm_gather_kernel<3><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in4, out4); break;
-    default: spmm_gather_kernel<4><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in4, out4); break;
+    case 1: ISLE_SPMM_LAUNCH(1); break;
+    case 2: ISLE_SPMM_LAUNCH(2); break;
+    case 3: ISLE_SPMM_LAUNCH(3); break;
+    default: ISLE_SPMM_LAUNCH(4); break;
     }
+#undef ISLE_SPMM_LAUNCH
     count_launch(c);
 }
 

@@ -78,14 +78,26 @@ def compute_thresholds(vals, rows, V: int, nz_docs: int, k: int):
          else z = next smaller distinct value
     Returns (zetas float32[V], new_nnzs).
     """
-    count_gr, count_eq = threshold_counts(nz_docs, k)
+    return thresholds_from_histogram(word_histogram(vals, rows, V), nz_docs, k)
+
+
+def word_histogram(vals, rows, V: int, bins: int = 0):
+    """hist[w, v] = #documents in which word w has rounded value v >= 1 (:378-387).  Additive over
+    disjoint document sets: the doc-sharded path sums these tables across ranks."""
     r = round_half_away(vals).astype(np.int64)
     rows = np.asarray(rows, dtype=np.int64)
     keep = r >= 1
     r, w = r[keep], rows[keep]
-    maxv = int(r.max(initial=1))
-    hist = np.zeros((V, maxv + 2), dtype=np.int64)
+    maxv = max(int(r.max(initial=1)) + 2, bins)
+    hist = np.zeros((V, maxv), dtype=np.int64)
     np.add.at(hist, (w, r), 1)
+    return hist
+
+
+def thresholds_from_histogram(hist, nz_docs: int, k: int):
+    """The rank rule of compute_thresholds (:389-481) on per-word histograms."""
+    V = hist.shape[0]
+    count_gr, count_eq = threshold_counts(nz_docs, k)
     zetas = np.ones(V, dtype=F32)
     new_nnzs = 0
     n_w = hist.sum(1)

@@ -4,6 +4,7 @@ fixtures.  Bars (BASELINE.json north star): thresholds and B bit-exact; singular
 within 1e-4 relative, principal angle < 1e-3; identical Lloyd assignments from identical
 projection and initial centers (ties excepted); objective within 1e-4."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -298,3 +299,20 @@ def test_spectral_core_end_to_end_c1(ctx, golden_c1, corpus_c1):
     assert abs(r.objective - obj_ref) / obj_ref < 2e-3
     assert r.centers.shape == (c.V, c.k)
     assert ctx.stat("launches") > 0
+
+
+@pytest.mark.gpu
+def test_document_sharded_run_matches_single_gpu():
+    """N = 2 ranks over NCCL vs one GPU (tests/multi_gpu_check.py); needs two visible GPUs."""
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "tests", "multi_gpu_check.py"), "c1"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
