@@ -79,6 +79,11 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            # nvidia-smi's start-up (NVML init on every GPU of the box) stalls CUDA calls of running
+            # processes for up to ~0.7 s: wait for its first sample so that never lands in a timed step
+            t_end = time.time() + 15.0
+            while time.time() < t_end and os.path.getsize(self.path) == 0 and self.proc.poll() is None:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 

@@ -55,6 +55,9 @@ static int create_common(isle_cuda_ctx **out, int device, int rank, int world, c
     try {
         ISLE_CUDA_CHECK(cudaSetDevice(device));
         ISLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        ISLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+        ISLE_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+        ISLE_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
         {   // keep freed scratch memory cached in the pool instead of returning it to the driver
             cudaMemPool_t pool;
             ISLE_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -125,6 +128,9 @@ void isle_cuda_destroy(isle_cuda_ctx *h)
     if (c.comm) ncclCommDestroy(c.comm);
 #endif
     if (c.timer0) { cudaEventDestroy(c.timer0); cudaEventDestroy(c.timer1); }
+    if (c.stream2) { cudaStreamSynchronize(c.stream2); cudaStreamDestroy(c.stream2); }
+    if (c.ev_fork) cudaEventDestroy(c.ev_fork);
+    if (c.ev_join) cudaEventDestroy(c.ev_join);
     if (c.cusolver) cusolverDnDestroy(c.cusolver);
     if (c.cublas) cublasDestroy(c.cublas);
     // device buffers are released by the DevBuf destructors inside Ctx
@@ -286,6 +292,8 @@ int isle_cuda_get_stat(isle_cuda_ctx *h, const char *name, double *out)
         if (n == "launches") { *out = c.launches; return; }
         if (n == "nnz_B") { *out = (double)c.nnzB; return; }
         if (n == "D_B") { *out = (double)c.DB; return; }
+        if (n == "spmm_head_words") { *out = (double)c.H; return; }
+        if (n == "spmm_tail_nnz") { *out = (double)c.nnz_tail; return; }
         auto ci = c.counters.find(n);
         if (ci != c.counters.end()) { *out = ci->second; return; }
         const size_t us = n.rfind('_');
@@ -342,6 +350,8 @@ int isle_cuda_set_option(isle_cuda_ctx *h, const char *name, int value)
     return guarded(h, [&](Ctx &c) {
         ISLE_REQUIRE(name, ISLE_ERR_ARG, "set_option: bad arguments");
         c.options[name] = value;
+        // operator layout options take effect at the next build of the head/tail split
+        if (std::strncmp(name, "spmm_head", 9) == 0) c.have_csr = false;
     });
 }
 

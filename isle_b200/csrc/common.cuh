@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cublas_v2.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
 
@@ -106,6 +107,9 @@ struct KernelStat {
     double flops = 0.0;
 };
 
+constexpr int kHeadTile = 128;   // rows per tensor-core tile of the head engine (UMMA M)
+constexpr int kHeadChunk = 128;  // k per pipeline stage of the head engine
+
 struct WorkItem {          // one 4-lane group's share of a sparse pass
     uint32_t out_row;      // row of the dense output this item accumulates into
     uint32_t len;          // number of nonzeros
@@ -149,9 +153,24 @@ struct Ctx {
     bool have_csr = false;
     DevBuf<uint32_t> csr_col;              // [nnzB] doc of each nonzero, word-major
     DevBuf<int64_t> csr_off;               // [V+1]
-    DevBuf<WorkItem> items_bt, items_b;    // work lists for Y=B^T X and Z=B Y
+    DevBuf<WorkItem> items_bt, items_b;    // work lists for Y=B^T X and Z=B Y (tail part)
     size_t n_items_bt = 0, n_items_b = 0;
-    DevBuf<float> xs, ybuf, zbuf;          // padded row-major operands of the SpMM pair
+    DevBuf<float> xs, ybuf, zbuf;          // padded row-major operands of the SpMM pair (xs, zbuf in rank space)
+    // operator layout (spmm.cu): words relabelled by decreasing row length ("rank space"); the H
+    // most frequent words form the dense head (bitmaps + tcgen05, spmm_head.cu), the rest the tail
+    uint32_t H = 0;                        // head words, multiple of 128 (0: no head engine)
+    uint32_t DBpad = 0;                    // DB rounded up to 128
+    int64_t nnz_tail = 0;
+    DevBuf<uint32_t> rank_of, word_of_rank;   // [V]
+    DevBuf<uint32_t> t1_idx;               // doc-major tail: rank of each nonzero
+    DevBuf<int64_t> t1_off;                // [DB+1]
+    DevBuf<uint32_t> t2_idx;               // rank-major tail: doc of each nonzero
+    DevBuf<int64_t> t2_off;                // [V+1] (head ranks are empty rows)
+    DevBuf<uint4> xbfp, ybfp;              // one-sector (32-byte) copies of the operand rows, two 16-byte units per row
+    DevBuf<uint4> bits1, bits2;            // head bitmaps: (doc tile x rank chunk) and (rank tile x doc chunk)
+    DevBuf<__nv_bfloat16> xsplit, ysplit;  // 3-piece bf16 splits of the head rows of Xs / of Y, K-major [N][Kpad]
+    cudaStream_t stream2 = nullptr;        // head pass 2 runs beside the tail pass 2
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     // ---- eigen / projection state
     uint64_t k = 0;
@@ -222,6 +241,12 @@ float frobenius(Ctx &c);
 void build_csr(Ctx &c);
 // Z(V x b, column-major, ld=V) = B (B^T X); X column-major ld=V; both on the device.
 void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z);
+
+// ---- spmm_head.cu (dense head of the operator on tcgen05)
+int head_block_stride(int b);
+int head_split_rows(int b);
+void spmm_head_launch(Ctx &c, int b, const uint4 *bits, uint32_t num_mtiles, uint32_t NC, uint32_t nsplit,
+                      const __nv_bfloat16 *split, float *out, uint32_t m_valid, bool zero_out, cudaStream_t stream);
 
 // ---- blockks.cu
 void block_ks(Ctx &c, uint64_t k, int b, int max_restarts, float tol, uint64_t seed,

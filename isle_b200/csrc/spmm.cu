@@ -2,15 +2,20 @@
 //
 // Replaces MKL_SpSpTrProd (reference include/matUtils.h:14-419): the ctor's CSC->CSR copy by
 // sorting (:109-135) is a stable device radix sort of (word, doc) pairs; multiply()
-// (:336-365, two mkl_scsrmm passes) is two launches of one gather kernel:
+// (:336-365, two mkl_scsrmm passes) is
 //     pass 1   Y[d,:] = sum_{w in doc d}  Xs[w,:]          Xs = diag(sqrt_zeta) X
 //     pass 2   T[w,:] = sum_{d containing w} Y[d,:]        Z  = diag(sqrt_zeta) T
-// B is a 0/1 pattern scaled by sqrt_zeta per row, so no value stream is read:
-// 4 bytes per nonzero.  Dense operands are row-major with a fixed 16-float (64 B = two
-// 32 B sectors) row stride so a 4-lane group fetches one row with one float4 per lane.
-// Work is cut into items (row, first nnz, length <= ISLE_SPMM_CHUNK) sorted by decreasing
-// length, so the eight 4-lane groups of a warp run equally long loops despite Zipfian row
-// lengths; rows cut into several items finish with float4 atomics.
+// B is a 0/1 pattern scaled by sqrt_zeta per row, so no value stream is read.
+//
+// Layout.  Words are relabelled by decreasing row length ("rank space").  The H most frequent
+// words (density >= ~1 % of the documents; more than half of all nonzeros on Zipfian corpora) form
+// the dense HEAD, kept as bitmaps and multiplied on the tensor cores (spmm_head.cu).  The TAIL
+// keeps index lists (4 bytes per nonzero, doc-major for pass 1, rank-major for pass 2) and is
+// processed by the gather kernel below: dense operands are row-major with a fixed 16-float
+// (64 B = two 32 B sectors) row stride so a 4-lane group fetches one row with one float4 per lane.
+// Work is cut into items (row, first nnz, length <= kChunk) sorted by decreasing length, so the
+// eight 4-lane groups of a warp run equally long loops despite Zipfian row lengths;
+// rows cut into several items finish with float4 atomics.
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -20,7 +25,7 @@
 namespace isle {
 
 static constexpr int kStride = 16;          // floats per padded dense row
-static constexpr uint32_t kChunk = 2048;    // max nonzeros per work item
+static constexpr uint32_t kChunk = 256;     // max nonzeros per work item (bounds the serial length of a 4-lane group)
 static constexpr uint32_t kSplitFlag = 0x80000000u;
 
 // ------------------------------------------------------------------------------ CSR copy
@@ -127,6 +132,128 @@ static void build_items(Ctx &c, const int64_t *off, uint32_t nrows, DevBuf<WorkI
     ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }
 
+// ------------------------------------------------------------------- rank space, head / tail
+__global__ void row_len_kernel(const int64_t *__restrict__ off, uint32_t V, uint32_t *__restrict__ len,
+                               uint32_t *__restrict__ id)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= V) return;
+    len[w] = (uint32_t)(off[w + 1] - off[w]);
+    id[w] = w;
+}
+
+__global__ void scatter_rank_kernel(const uint32_t *__restrict__ word_of_rank, uint32_t V, uint32_t *__restrict__ rank_of)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < V) rank_of[word_of_rank[r]] = r;
+}
+
+// number of leading entries of the descending array `len` that are >= thr
+__global__ void count_ge_kernel(const uint32_t *__restrict__ len, uint32_t V, uint32_t thr, uint32_t *__restrict__ out)
+{
+    uint32_t lo = 0, hi = V;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (len[mid] >= thr) lo = mid + 1; else hi = mid;
+    }
+    *out = lo;
+}
+
+// lengths of the rank-major tail rows: head ranks become empty rows
+__global__ void tail_len_kernel(const uint32_t *__restrict__ len_sorted, uint32_t V, uint32_t H, uint32_t *__restrict__ out)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= V) out[r] = (r < H || r == V) ? 0u : len_sorted[r];
+}
+
+struct U32ToI64 {
+    __host__ __device__ int64_t operator()(uint32_t x) const { return (int64_t)x; }
+};
+
+static void scan_to_offsets(Ctx &c, uint32_t *cnt, size_t n_plus_1, int64_t *off)
+{
+    auto it = cub::TransformInputIterator<int64_t, U32ToI64, uint32_t *>(cnt, U32ToI64());
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, it, off, (int)n_plus_1, c.stream);
+    DevBuf<uint8_t> tmp(tb);
+    ISLE_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, off, (int)n_plus_1, c.stream));
+    count_launch(c);
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));   // tmp is released on return
+}
+
+// tail nonzeros per document (warp per document)
+__global__ void __launch_bounds__(256)
+doc_tail_count_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ row, const uint32_t *__restrict__ rank_of,
+                      uint32_t H, uint32_t DB, uint32_t *__restrict__ cnt)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (; d < DB; d += nw) {
+        const int64_t b = off[d], e = off[d + 1];
+        uint32_t n = 0;
+        for (int64_t p = b + lane; p < e; p += 32) n += (__ldg(rank_of + row[p]) >= H) ? 1u : 0u;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        if (lane == 0) cnt[d] = n;
+    }
+}
+
+// Writes the doc-major tail list (ranks, document order preserved) and sets the head bits of the
+// document in both bitmaps.  bit position of element k inside its 32-bit word: (k>>1) + 16 (k&1),
+// the order expand_word() (spmm_head.cu) unpacks.
+__device__ __forceinline__ uint32_t head_bit(uint32_t k) { return 1u << (((k & 31u) >> 1) + ((k & 1u) << 4)); }
+
+__global__ void __launch_bounds__(256)
+doc_split_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ row, const uint32_t *__restrict__ rank_of,
+                 uint32_t H, uint32_t DB, uint32_t NC1, uint32_t NC2, const int64_t *__restrict__ t1_off,
+                 uint32_t *__restrict__ t1_idx, uint32_t *__restrict__ bits1, uint32_t *__restrict__ bits2)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (; d < DB; d += nw) {
+        const int64_t b = off[d], e = off[d + 1];
+        int64_t out = t1_off[d];
+        for (int64_t p0 = b; p0 < e; p0 += 32) {
+            const int64_t p = p0 + lane;
+            bool tail = false;
+            uint32_t r = 0;
+            if (p < e) {
+                r = __ldg(rank_of + row[p]);
+                tail = r >= H;
+                if (!tail) {
+                    // bits1: rows = documents, k = rank;  bits2: rows = ranks, k = document
+                    const size_t i1 = ((((size_t)(d >> 7) * NC1 + (r >> 7)) * kHeadTile + (d & 127u)) << 2) + ((r >> 5) & 3u);
+                    const size_t i2 = ((((size_t)(r >> 7) * NC2 + (d >> 7)) * kHeadTile + (r & 127u)) << 2) + ((d >> 5) & 3u);
+                    atomicOr(bits1 + i1, head_bit(r));
+                    atomicOr(bits2 + i2, head_bit(d));
+                }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, tail);
+            if (tail) t1_idx[out + __popc(m & ((1u << lane) - 1u))] = r;
+            out += __popc(m);
+        }
+    }
+}
+
+// rank-major tail list: row r >= H is the word-major row of word_of_rank[r] (warp per row)
+__global__ void __launch_bounds__(256)
+rank_rows_copy_kernel(const int64_t *__restrict__ csr_off, const uint32_t *__restrict__ csr_col,
+                      const uint32_t *__restrict__ word_of_rank, uint32_t H, uint32_t V,
+                      const int64_t *__restrict__ t2_off, uint32_t *__restrict__ t2_idx)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t r = H + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (; r < V; r += nw) {
+        const uint32_t w = word_of_rank[r];
+        const int64_t b = csr_off[w], n = csr_off[w + 1] - b;
+        const int64_t o = t2_off[r];
+        for (int64_t i = lane; i < n; i += 32) t2_idx[o + i] = csr_col[b + i];
+    }
+}
+
 void build_csr(Ctx &c)
 {
     ISLE_REQUIRE(c.have_B, ISLE_ERR_ARG, "build_csr: build_B first");
@@ -134,12 +261,13 @@ void build_csr(Ctx &c)
     StatScope s(c, "csr_build", (double)c.nnzB * 24.0);
     const int64_t n = c.nnzB;
     const uint32_t V = (uint32_t)c.V, DB = (uint32_t)c.DB;
+    const unsigned wgrid = grid_for((size_t)std::max<uint32_t>(DB, 1) * 32, 256, c.num_sms * 16);
     c.csr_col.alloc((size_t)n);
     c.csr_off.alloc((size_t)V + 1);
     {
         DevBuf<uint32_t> doc_of((size_t)n), keys_out((size_t)n);
         if (DB) {
-            fill_doc_ids_kernel<<<grid_for((size_t)DB * 32, 256, c.num_sms * 16), 256, 0, c.stream>>>(c.b_off.p, DB, doc_of.p);
+            fill_doc_ids_kernel<<<wgrid, 256, 0, c.stream>>>(c.b_off.p, DB, doc_of.p);
             count_launch(c);
         }
         int bits = 1;
@@ -153,21 +281,108 @@ void build_csr(Ctx &c)
         count_launch(c, 2);
         ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
     }
-    build_items(c, c.b_off.p, DB, c.items_bt, c.n_items_bt);
-    build_items(c, c.csr_off.p, V, c.items_b, c.n_items_b);
+
+    // ---- rank space: words by decreasing row length
+    c.rank_of.alloc(V);
+    c.word_of_rank.alloc(V);
+    DevBuf<uint32_t> len(V), len_sorted(V), ids(V);
+    row_len_kernel<<<(V + 255) / 256, 256, 0, c.stream>>>(c.csr_off.p, V, len.p, ids.p);
+    {
+        size_t ts = 0;
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, ts, len.p, len_sorted.p, ids.p, c.word_of_rank.p, (int)V, 0, 32, c.stream);
+        DevBuf<uint8_t> tmp(ts);
+        ISLE_CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(tmp.p, ts, len.p, len_sorted.p, ids.p, c.word_of_rank.p, (int)V, 0, 32, c.stream));
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    }
+    scatter_rank_kernel<<<(V + 255) / 256, 256, 0, c.stream>>>(c.word_of_rank.p, V, c.rank_of.p);
+    count_launch(c, 3);
+
+    // ---- head size: words present in at least `density` of the documents, whole 128-row tiles
+    uint32_t H = 0;
+    if (c.opt("spmm_head", 1) && DB >= 1) {
+        const double dens = c.opt("spmm_head_density_ppm", 12000) * 1e-6;
+        const uint32_t thr = (uint32_t)std::max(1.0, std::ceil(dens * (double)DB));
+        DevBuf<uint32_t> dcnt(1);
+        count_ge_kernel<<<1, 1, 0, c.stream>>>(len_sorted.p, V, thr, dcnt.p);
+        count_launch(c);
+        uint32_t h0 = 0;
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(&h0, dcnt.p, 4, cudaMemcpyDeviceToHost, c.stream));
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        const uint32_t hmax = (uint32_t)std::max(0, c.opt("spmm_head_max", 4096));
+        H = std::min(h0, hmax) / kHeadTile * kHeadTile;
+    }
+    c.H = H;
+    c.DBpad = (DB + kHeadTile - 1) / kHeadTile * kHeadTile;
+    const uint32_t NC1 = H / kHeadChunk, NC2 = c.DBpad / kHeadChunk;
+
+    // ---- doc-major tail list + head bitmaps
+    c.t1_off.alloc((size_t)DB + 1);
+    {
+        DevBuf<uint32_t> cnt((size_t)DB + 1);
+        ISLE_CUDA_CHECK(cudaMemsetAsync(cnt.p + DB, 0, 4, c.stream));
+        if (DB) doc_tail_count_kernel<<<wgrid, 256, 0, c.stream>>>(c.b_off.p, c.b_row.p, c.rank_of.p, H, DB, cnt.p);
+        count_launch(c);
+        scan_to_offsets(c, cnt.p, (size_t)DB + 1, c.t1_off.p);
+    }
+    int64_t nnz_tail = 0;
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(&nnz_tail, c.t1_off.p + DB, 8, cudaMemcpyDeviceToHost, c.stream));
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.nnz_tail = nnz_tail;
+    c.t1_idx.alloc((size_t)nnz_tail);
+    const size_t nbits = (size_t)c.DBpad * H / kHeadChunk;       // uint4 entries per bitmap
+    c.bits1.alloc(nbits);
+    c.bits2.alloc(nbits);
+    if (nbits) {
+        ISLE_CUDA_CHECK(cudaMemsetAsync(c.bits1.p, 0, c.bits1.bytes(), c.stream));
+        ISLE_CUDA_CHECK(cudaMemsetAsync(c.bits2.p, 0, c.bits2.bytes(), c.stream));
+    }
+    if (DB) {
+        doc_split_kernel<<<wgrid, 256, 0, c.stream>>>(c.b_off.p, c.b_row.p, c.rank_of.p, H, DB, NC1, NC2, c.t1_off.p, c.t1_idx.p,
+                                                      reinterpret_cast<uint32_t *>(c.bits1.p), reinterpret_cast<uint32_t *>(c.bits2.p));
+        count_launch(c);
+    }
+
+    // ---- rank-major tail list
+    c.t2_off.alloc((size_t)V + 1);
+    {
+        DevBuf<uint32_t> cnt((size_t)V + 1);
+        tail_len_kernel<<<(V + 1 + 255) / 256, 256, 0, c.stream>>>(len_sorted.p, V, H, cnt.p);
+        count_launch(c);
+        scan_to_offsets(c, cnt.p, (size_t)V + 1, c.t2_off.p);
+    }
+    c.t2_idx.alloc((size_t)nnz_tail);
+    if (V > H) {
+        rank_rows_copy_kernel<<<grid_for((size_t)(V - H) * 32, 256, c.num_sms * 16), 256, 0, c.stream>>>(
+            c.csr_off.p, c.csr_col.p, c.word_of_rank.p, H, V, c.t2_off.p, c.t2_idx.p);
+        count_launch(c);
+    }
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.csr_col.release();    // only the rank-major copy is used from here on
+
+    build_items(c, c.t1_off.p, DB, c.items_bt, c.n_items_bt);
+    build_items(c, c.t2_off.p, V, c.items_b, c.n_items_b);
     c.xs.alloc((size_t)V * kStride);
-    c.ybuf.alloc((size_t)std::max<uint64_t>(DB, 1) * kStride);
+    c.ybuf.alloc((size_t)std::max<uint32_t>(c.DBpad, 1) * kStride);
     c.zbuf.alloc((size_t)V * kStride);
+    c.xbfp.alloc((size_t)V * 2);
+    c.ybfp.alloc((size_t)std::max<uint32_t>(c.DBpad, 1) * 2);
+    if (H) {
+        const size_t nrows = 48;    // 3 bf16 pieces x up to 16 columns
+        c.xsplit.alloc(nrows * H);
+        c.ysplit.alloc(nrows * c.DBpad);
+        ISLE_CUDA_CHECK(cudaMemsetAsync(c.xsplit.p, 0, c.xsplit.bytes(), c.stream));
+        ISLE_CUDA_CHECK(cudaMemsetAsync(c.ysplit.p, 0, c.ysplit.bytes(), c.stream));
+    }
     c.have_csr = true;
 }
 
 // --------------------------------------------------------------------------- the gather pass
 // One 4-lane group per work item; lane `sub` owns floats [4 sub, 4 sub + 4) of the row.
 // Per step each lane loads one index (coalesced 16 B per group), indices are exchanged by
-// shuffle and four independent float4 gathers are issued before they are summed, in a fixed
+// shuffle and eight independent float4 gathers are issued before they are summed, in a fixed
 // order so that results are run-to-run deterministic for unsplit rows.
 // Index stream loads: read once, so optionally kept out of L1 (ld.global.nc.L1::no_allocate) to leave
-// the cache to the gathered dense rows.
+// the cache to the gathered dense rows.  ADD: the output row already holds the head part.
 template <bool NOALLOC>
 __device__ __forceinline__ uint32_t ld_idx(const uint32_t *p)
 {
@@ -179,7 +394,7 @@ __device__ __forceinline__ uint32_t ld_idx(const uint32_t *p)
     return __ldg(p);
 }
 
-template <int NCH, bool NOALLOC>
+template <int NCH, bool NOALLOC, bool ADD>
 __global__ void __launch_bounds__(256)
 spmm_gather_kernel(const WorkItem *__restrict__ items, size_t n_items, const uint32_t *__restrict__ idx,
                    const float4 *__restrict__ in, float4 *__restrict__ out)
@@ -224,35 +439,195 @@ spmm_gather_kernel(const WorkItem *__restrict__ items, size_t n_items, const uin
     }
     if (!active) return;
     float4 *o = out + (size_t)it.out_row * 4 + sub;
-    if (it.len & kSplitFlag) atomicAdd(o, acc);   // sm_90+: 16-byte vector atomic (RED.128)
-    else *o = acc;
+    if (it.len & kSplitFlag) {
+        atomicAdd(o, acc);   // sm_90+: 16-byte vector atomic (RED.128)
+    } else if (ADD) {
+        const float4 h = *o;
+        *o = make_float4(h.x + acc.x, h.y + acc.y, h.z + acc.z, h.w + acc.w);
+    } else {
+        *o = acc;
+    }
 }
 
-// Xs[w, j] = sqrt_zeta[w] * X[w + j ld]  (j < b), zero padded to 16 floats.
-__global__ void __launch_bounds__(256)
-pack_scaled_kernel(const float *__restrict__ X, size_t ld, uint32_t n, int b,
-                   const float *__restrict__ scale, float4 *__restrict__ out)
+// ------------------------------------------------------------- one-sector operand rows (BFP)
+// For block sizes <= 10 the gathered operand rows are stored as 32 bytes = ONE sector instead of
+// a padded 64-byte fp32 row, which halves the L2->SM traffic that bounds the tail passes.  A row
+// is two 16-byte units of five columns; a unit holds five 24-bit two's-complement mantissas
+// (bytes 0..14) and one shared power-of-two scale (byte 15 = the float exponent field of
+// scale * 2^-8, 0 for an all-zero unit).  The largest element of a unit keeps a full fp32
+// significand (error <= 2^-24 of the unit maximum per element).
+__device__ __forceinline__ uint4 bfp_encode5(const float *v)
 {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n) return;
+    float m = 0.f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) m = fmaxf(m, fabsf(v[j]));
+    const int em = (int)((__float_as_uint(m) >> 23) & 0xFFu);     // exponent field of the maximum
+    if (em < 31 || em == 255) return make_uint4(0u, 0u, 0u, 0u);  // zero / denormal-range (or non-finite) unit
+    const int es = em - 22;                                        // scale s = 2^(es-127): |v| / s < 2^23
+    const float inv_s = __uint_as_float((uint32_t)(254 - es) << 23);
+    int q[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) q[j] = max(-8388607, min(8388607, __float2int_rn(v[j] * inv_s)));
+    uint4 w;
+    w.x = ((uint32_t)q[0] & 0xFFFFFFu) | ((uint32_t)q[1] << 24);
+    w.y = (((uint32_t)q[1] >> 8) & 0xFFFFu) | ((uint32_t)q[2] << 16);
+    w.z = (((uint32_t)q[2] >> 16) & 0xFFu) | ((uint32_t)q[3] << 8);
+    w.w = ((uint32_t)q[4] & 0xFFFFFFu) | ((uint32_t)(es - 8) << 24);
+    return w;
+}
+
+// acc[j] += value j of the unit
+__device__ __forceinline__ void bfp_accum5(const uint4 w, float *acc)
+{
+    const float sc = __uint_as_float((w.w >> 1) & 0x7F800000u);
+    acc[0] = fmaf((float)(int)(w.x << 8), sc, acc[0]);
+    acc[1] = fmaf((float)(int)(__funnelshift_r(w.x, w.y, 16) & 0xFFFFFF00u), sc, acc[1]);
+    acc[2] = fmaf((float)(int)(__funnelshift_r(w.y, w.z, 8) & 0xFFFFFF00u), sc, acc[2]);
+    acc[3] = fmaf((float)(int)(w.z & 0xFFFFFF00u), sc, acc[3]);
+    acc[4] = fmaf((float)(int)(w.w << 8), sc, acc[4]);
+}
+
+// One 4-lane group per work item = two lane pairs; a pair gathers the rows of the four indices its
+// two lanes loaded, lane (sub & 1) taking unit (sub & 1) of each row with one 16-byte load, so a
+// warp instruction fetches 16 whole sectors.  The two pairs' sums are combined by shuffle; lanes 0 and
+// 1 of the group then own columns 0..4 and 5..9 of the output row (fp32, 16-float stride).
+template <bool ADD>
+__global__ void __launch_bounds__(256)
+spmm_gather_bfp_kernel(const WorkItem *__restrict__ items, size_t n_items, const uint32_t *__restrict__ idx,
+                       const uint4 *__restrict__ in, float *__restrict__ out, int b)
+{
+    const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int sub = threadIdx.x & 3, u = sub & 1;
+    const unsigned gmask = 0xFu << (threadIdx.x & 28);   // groups of a warp run loops of different lengths
+    if (g >= n_items) return;     // whole groups exit together
+    const WorkItem it = items[g];
+    const uint32_t len = it.len & ~kSplitFlag;
+    const uint32_t *p = idx + it.begin;
+    const uint4 *base = in + u;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t j = 0;
+    for (; j + 8 <= len; j += 8) {
+        const uint32_t i0 = ld_idx<true>(p + j + sub), i1 = ld_idx<true>(p + j + 4 + sub);
+        const uint32_t k0 = __shfl_xor_sync(gmask, i0, 1), k1 = __shfl_xor_sync(gmask, i1, 1);
+        // the pair's four rows in stream order: (even lane's, odd lane's) x (first, second load)
+        const uint32_t ra = u ? k0 : i0, rb = u ? i0 : k0, rc = u ? k1 : i1, rd = u ? i1 : k1;
+        const uint4 wa = __ldg(base + (size_t)ra * 2), wb = __ldg(base + (size_t)rb * 2);
+        const uint4 wc = __ldg(base + (size_t)rc * 2), wd = __ldg(base + (size_t)rd * 2);
+        bfp_accum5(wa, acc); bfp_accum5(wb, acc); bfp_accum5(wc, acc); bfp_accum5(wd, acc);
+    }
+    if (j < len) {
+        const uint32_t n = len - j;     // 1..7 left: positions sub and 4 + sub
+        const uint32_t i0 = (uint32_t)sub < n ? ld_idx<true>(p + j + sub) : 0u;
+        const uint32_t i1 = (uint32_t)sub + 4 < n ? ld_idx<true>(p + j + 4 + sub) : 0u;
+        const uint32_t k0 = __shfl_xor_sync(gmask, i0, 1), k1 = __shfl_xor_sync(gmask, i1, 1);
+        const uint32_t pe = (uint32_t)(sub & 2), po = pe + 1;       // stream positions of the pair's even / odd lane
+        const uint32_t ra = u ? k0 : i0, rb = u ? i0 : k0, rc = u ? k1 : i1, rd = u ? i1 : k1;
+        if (pe < n) bfp_accum5(__ldg(base + (size_t)ra * 2), acc);
+        if (po < n) bfp_accum5(__ldg(base + (size_t)rb * 2), acc);
+        if (pe + 4 < n) bfp_accum5(__ldg(base + (size_t)rc * 2), acc);
+        if (po + 4 < n) bfp_accum5(__ldg(base + (size_t)rd * 2), acc);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc[k] += __shfl_xor_sync(gmask, acc[k], 2);
+    if (sub >= 2) return;
+    float *o = out + (size_t)it.out_row * kStride + 5 * u;
+    const int ncol = min(5, b - 5 * u);
+    if (it.len & kSplitFlag) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (k < ncol) atomicAdd(o + k, acc[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (k < ncol) o[k] = ADD ? o[k] + acc[k] : acc[k];
+    }
+}
+
+__device__ __forceinline__ void split3(float v, __nv_bfloat16 &h, __nv_bfloat16 &m, __nv_bfloat16 &l)
+{
+    h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);          // exact
+    m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);         // exact
+    l = __float2bfloat16_rn(r2);
+}
+
+// Rank space: Xs[r, j] = sqrt_zeta[w] * X[w + j ld], w = word_of_rank[r]  (j < b), zero padded to 16
+// floats; head ranks are also written as three bf16 pieces, K-major: xsplit[(piece*BS + j) * H + r].
+__global__ void __launch_bounds__(256)
+pack_scaled_kernel(const float *__restrict__ X, size_t ld, uint32_t n, int b, const float *__restrict__ scale,
+                   const uint32_t *__restrict__ word_of_rank, float4 *__restrict__ out, uint4 *__restrict__ out_bfp,
+                   uint32_t H, int BS, __nv_bfloat16 *__restrict__ xsplit)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t w = word_of_rank[r];
     const float s = scale ? scale[w] : 1.0f;
     float v[kStride];
 #pragma unroll
     for (int j = 0; j < kStride; ++j) v[j] = (j < b) ? s * X[w + (size_t)j * ld] : 0.0f;
+    if (out_bfp) {      // b <= 10: one-sector rows
+        out_bfp[(size_t)r * 2] = bfp_encode5(v);
+        out_bfp[(size_t)r * 2 + 1] = bfp_encode5(v + 5);
+    } else {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-        out[(size_t)w * 4 + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < 4; ++q)
+            out[(size_t)r * 4 + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    if (r < H) {
+#pragma unroll
+        for (int j = 0; j < kStride; ++j) {
+            if (j < b) {
+                __nv_bfloat16 h, m, l;
+                split3(v[j], h, m, l);
+                xsplit[(size_t)j * H + r] = h;
+                xsplit[(size_t)(BS + j) * H + r] = m;
+                xsplit[(size_t)(2 * BS + j) * H + r] = l;
+            }
+        }
+    }
 }
 
-// Z[w + j ld] = sqrt_zeta[w] * T[w, j]
+// ysplit[(piece*BS + j) * DBpad + d] = pieces of Y[d, j] (head engine, when ysplit != NULL);
+// ybfp[d] = one-sector copy of Y[d, :] (tail gather of pass 2, when ybfp != NULL)
+__global__ void __launch_bounds__(256)
+ysplit_kernel(const float4 *__restrict__ Y, uint32_t DB, uint32_t DBpad, int b, int BS, __nv_bfloat16 *__restrict__ ysplit,
+              uint4 *__restrict__ ybfp)
+{
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= DB) return;
+    float v[kStride];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 t = Y[(size_t)d * 4 + q];
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+    if (ybfp) {
+        ybfp[(size_t)d * 2] = bfp_encode5(v);
+        ybfp[(size_t)d * 2 + 1] = bfp_encode5(v + 5);
+    }
+    if (!ysplit) return;
+#pragma unroll
+    for (int j = 0; j < kStride; ++j) {
+        if (j < b) {
+            __nv_bfloat16 h, m, l;
+            split3(v[j], h, m, l);
+            ysplit[(size_t)j * DBpad + d] = h;
+            ysplit[(size_t)(BS + j) * DBpad + d] = m;
+            ysplit[(size_t)(2 * BS + j) * DBpad + d] = l;
+        }
+    }
+}
+
+// Z[w + j ld] = sqrt_zeta[w] * T[rank_of[w], j]
 __global__ void __launch_bounds__(256)
 unpack_scaled_kernel(const float *__restrict__ T, uint32_t n, int b, const float *__restrict__ scale,
-                     float *__restrict__ Z, size_t ld)
+                     const uint32_t *__restrict__ rank_of, float *__restrict__ Z, size_t ld)
 {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n) return;
     const float s = scale ? scale[w] : 1.0f;
-    const float4 *t4 = reinterpret_cast<const float4 *>(T) + (size_t)w * 4;
+    const float4 *t4 = reinterpret_cast<const float4 *>(T) + (size_t)rank_of[w] * 4;
     float v[kStride];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -264,7 +639,7 @@ unpack_scaled_kernel(const float *__restrict__ T, uint32_t n, int b, const float
         if (j < b) Z[w + (size_t)j * ld] = s * v[j];
 }
 
-static void launch_gather(Ctx &c, int nch, const WorkItem *items, size_t n_items, const uint32_t *idx,
+static void launch_gather(Ctx &c, int nch, bool add, const WorkItem *items, size_t n_items, const uint32_t *idx,
                           const float *in, float *out)
 {
     if (!n_items) return;
@@ -272,10 +647,11 @@ static void launch_gather(Ctx &c, int nch, const WorkItem *items, size_t n_items
     const float4 *in4 = reinterpret_cast<const float4 *>(in);
     float4 *out4 = reinterpret_cast<float4 *>(out);
     const bool na = c.opt("spmm_idx_noalloc", 1) != 0;
-#define ISLE_SPMM_LAUNCH(N)                                                                                    \
-    do {                                                                                                       \
-        if (na) spmm_gather_kernel<N, true><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in4, out4);       \
-        else spmm_gather_kernel<N, false><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in4, out4);         \
+#define ISLE_SPMM_LAUNCH(N)                                                                                           \
+    do {                                                                                                              \
+        if (add) spmm_gather_kernel<N, true, true><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in4, out4);        \
+        else if (na) spmm_gather_kernel<N, true, false><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in4, out4);   \
+        else spmm_gather_kernel<N, false, false><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in4, out4);          \
     } while (0)
     switch (nch) {
     case 1: ISLE_SPMM_LAUNCH(1); break;
@@ -287,34 +663,90 @@ static void launch_gather(Ctx &c, int nch, const WorkItem *items, size_t n_items
     count_launch(c);
 }
 
+static void launch_gather_bfp(Ctx &c, int b, bool add, const WorkItem *items, size_t n_items, const uint32_t *idx,
+                              const uint4 *in, float *out)
+{
+    if (!n_items) return;
+    const unsigned grid = (unsigned)((n_items * 4 + 255) / 256);
+    if (add) spmm_gather_bfp_kernel<true><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in, out, b);
+    else spmm_gather_bfp_kernel<false><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in, out, b);
+    count_launch(c);
+}
+
 void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z)
 {
     ISLE_REQUIRE(c.have_B, ISLE_ERR_ARG, "spsptr_multiply: build_B first");
     ISLE_REQUIRE(b >= 1 && b <= kStride, ISLE_ERR_ARG, "spsptr_multiply: block size must be in [1,16]");
     build_csr(c);
-    const uint32_t V = (uint32_t)c.V, DB = (uint32_t)c.DB;
+    const uint32_t V = (uint32_t)c.V, DB = (uint32_t)c.DB, H = c.H;
     const int nch = (b + 3) / 4;
+    const int BS = head_block_stride(b);
     c.counters["ks_ops"] += 1.0;
 
-    pack_scaled_kernel<<<(V + 255) / 256, 256, 0, c.stream>>>(X, (size_t)V, V, b, c.sqrt_zeta.p,
-                                                               reinterpret_cast<float4 *>(c.xs.p));
+    // block sizes <= 10 gather one-sector (32-byte) operand rows; wider blocks use padded fp32 rows
+    const bool bfp = b <= 10 && c.opt("spmm_bfp", 1) != 0;
+    pack_scaled_kernel<<<(V + 255) / 256, 256, 0, c.stream>>>(X, (size_t)V, V, b, c.sqrt_zeta.p, c.word_of_rank.p,
+                                                               reinterpret_cast<float4 *>(c.xs.p), bfp ? c.xbfp.p : nullptr, H, BS,
+                                                               c.xsplit.p);
     count_launch(c);
-    // Every doc of B has >= 1 nonzero and is never split unless longer than kChunk: only then
-    // does Y need zeroing; word rows are split routinely (Zipf head), so T is always zeroed.
-    if (c.n_items_bt != (size_t)DB) ISLE_CUDA_CHECK(cudaMemsetAsync(c.ybuf.p, 0, c.ybuf.bytes(), c.stream));
+    // T is always zeroed: word rows are split routinely and the head adds partial sums atomically.
     ISLE_CUDA_CHECK(cudaMemsetAsync(c.zbuf.p, 0, c.zbuf.bytes(), c.stream));
     {
         // bytes_pass = nnz*4 + (rows+1)*8 + dense_in*4 + dense_out*4
         StatScope s(c, "spmm_bt", (double)c.nnzB * 4.0 + ((double)DB + 1) * 8.0 + ((double)V + DB) * b * 4.0,
                     2.0 * c.nnzB * b);
-        launch_gather(c, nch, c.items_bt.p, c.n_items_bt, c.b_row.p, c.xs.p, c.ybuf.p);
+        if (H) {
+            {
+                StatScope sh(c, "spmm_head1");
+                // every row of Y is written (store mode): Y = head part
+                spmm_head_launch(c, b, c.bits1.p, c.DBpad / kHeadTile, H / kHeadChunk, 1, c.xsplit.p, c.ybuf.p, DB, true, c.stream);
+            }
+            StatScope st(c, "spmm_tail1");
+            if (bfp) launch_gather_bfp(c, b, true, c.items_bt.p, c.n_items_bt, c.t1_idx.p, c.xbfp.p, c.ybuf.p);
+            else launch_gather(c, nch, true, c.items_bt.p, c.n_items_bt, c.t1_idx.p, c.xs.p, c.ybuf.p);
+        } else {
+            // a document without items (or split into several), and the columns >= b, need zeroed rows
+            if (bfp || c.n_items_bt != (size_t)DB) ISLE_CUDA_CHECK(cudaMemsetAsync(c.ybuf.p, 0, c.ybuf.bytes(), c.stream));
+            if (bfp) launch_gather_bfp(c, b, false, c.items_bt.p, c.n_items_bt, c.t1_idx.p, c.xbfp.p, c.ybuf.p);
+            else launch_gather(c, nch, false, c.items_bt.p, c.n_items_bt, c.t1_idx.p, c.xs.p, c.ybuf.p);
+        }
     }
     {
         StatScope s(c, "spmm_b", (double)c.nnzB * 4.0 + ((double)V + 1) * 8.0 + ((double)V + DB) * b * 4.0,
                     2.0 * c.nnzB * b);
-        launch_gather(c, nch, c.items_b.p, c.n_items_b, c.csr_col.p, c.ybuf.p, c.zbuf.p);
+        if ((H || bfp) && DB) {
+            ysplit_kernel<<<(DB + 255) / 256, 256, 0, c.stream>>>(reinterpret_cast<const float4 *>(c.ybuf.p), DB, c.DBpad, b, BS,
+                                                                  H ? c.ysplit.p : nullptr, bfp ? c.ybfp.p : nullptr);
+            count_launch(c);
+        }
+        if (H) {
+            const uint32_t mt = H / kHeadTile, NC2 = c.DBpad / kHeadChunk;
+            const uint32_t nsplit = std::max<uint32_t>(1, (uint32_t)c.num_sms / mt);   // one wave of jobs
+            const bool fork = c.opt("spmm_fork", 1) != 0;
+            if (fork) {
+                // the head and the tail of pass 2 write disjoint rows of T: run them side by side
+                ISLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
+                ISLE_CUDA_CHECK(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
+                spmm_head_launch(c, b, c.bits2.p, mt, NC2, nsplit, c.ysplit.p, c.zbuf.p, H, false, c.stream2);
+                ISLE_CUDA_CHECK(cudaEventRecord(c.ev_join, c.stream2));
+                if (bfp) launch_gather_bfp(c, b, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybfp.p, c.zbuf.p);
+                else launch_gather(c, nch, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybuf.p, c.zbuf.p);
+                ISLE_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
+            } else {
+                {
+                    StatScope sh(c, "spmm_head2");
+                    spmm_head_launch(c, b, c.bits2.p, mt, NC2, nsplit, c.ysplit.p, c.zbuf.p, H, false, c.stream);
+                }
+                StatScope st(c, "spmm_tail2");
+                if (bfp) launch_gather_bfp(c, b, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybfp.p, c.zbuf.p);
+                else launch_gather(c, nch, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybuf.p, c.zbuf.p);
+            }
+        } else {
+            if (bfp) launch_gather_bfp(c, b, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybfp.p, c.zbuf.p);
+            else launch_gather(c, nch, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybuf.p, c.zbuf.p);
+        }
     }
-    unpack_scaled_kernel<<<(V + 255) / 256, 256, 0, c.stream>>>(c.zbuf.p, V, b, c.sqrt_zeta.p, Z, (size_t)V);
+    unpack_scaled_kernel<<<(V + 255) / 256, 256, 0, c.stream>>>(c.zbuf.p, V, b, c.sqrt_zeta.p, c.rank_of.p, Z, (size_t)V);
     count_launch(c);
     if (c.world > 1) {
         // doc-sharded: Z = sum over ranks of B_g (B_g^T X)   
