@@ -391,7 +391,7 @@ cholqr2_kernel(CholQrParams p)
 // N = b <= 16, for which a library GEMM spends its time in split-K bookkeeping.
 //   wtf:   C = W^T F   per-chunk partials (fixed order -> deterministic) + ordered reduce
 //   fsub:  F -= W C,   one thread per row of F, C staged in shared memory
-static constexpr int kWtfChunk = 512;    // rows of W per CTA
+static constexpr int kWtfChunk = 1024;   // rows of W per CTA
 static constexpr int kWtfCols = 32;      // columns of W per CTA (4 per warp)
 
 template <int BP>
@@ -563,7 +563,7 @@ struct KsState {
         ISLE_CUDA_CHECK(cudaFuncSetAttribute(cholqr2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholDynSmem));
         ISLE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cholqr2_kernel, 256, kCholDynSmem));
         ISLE_REQUIRE(per_sm >= 1, ISLE_ERR_CUDA, "cholqr2_kernel cannot be made resident");
-        chol_grid = std::max(1, std::min((int)((n + 15) / 16), c.num_sms * std::min(per_sm, 4)));
+        chol_grid = std::max(1, std::min((int)((n + 15) / 16), c.num_sms));   // every CTA re-sums all partials: keep them few
         cpart.alloc((size_t)2 * chol_grid * 256);
         const int chunks = (int)((n + kWtfChunk - 1) / kWtfChunk);
         wpart.alloc((size_t)chunks * ncv * kMaxB);

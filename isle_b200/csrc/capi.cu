@@ -14,6 +14,23 @@ struct isle_cuda_ctx {
 
 static thread_local std::string g_create_error;
 
+// timeout record of the tensor-core head kernel (spmm_head.cu), if it left one
+static std::string head_diag_text(const Ctx &c)
+{
+    const volatile uint32_t *d = c.head_diag_host;
+    if (!d) return "";
+    std::string out;
+    for (int slot = 0; slot < 12; ++slot) {
+        const volatile uint32_t *r = d + slot * 5;
+        if (r[0] == 0) continue;
+        char buf[160];
+        std::snprintf(buf, sizeof(buf), " [spmm_head_kernel wait timed out: code=0x%x block=%u thread=%u a=%u b=%u]", r[0] - 1, r[1],
+                      r[2], r[3], r[4]);
+        out += buf;
+    }
+    return out;
+}
+
 template <class F>
 static int guarded(isle_cuda_ctx *h, F &&f)
 {
@@ -21,13 +38,14 @@ static int guarded(isle_cuda_ctx *h, F &&f)
     try {
         ISLE_CUDA_CHECK(cudaSetDevice(h->c.device));
         tls_stream() = h->c.stream;
+        tls_cache() = &h->c.cache;
         f(h->c);
         return ISLE_OK;
     } catch (const Error &e) {
-        h->c.last_error = e.what();
+        h->c.last_error = e.what() + head_diag_text(h->c);
         return e.code;
     } catch (const std::exception &e) {
-        h->c.last_error = e.what();
+        h->c.last_error = e.what() + head_diag_text(h->c);
         return ISLE_ERR_CUDA;
     }
 }
@@ -58,11 +76,12 @@ static int create_common(isle_cuda_ctx **out, int device, int rank, int world, c
         ISLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
         ISLE_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
         ISLE_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
-        {   // keep freed scratch memory cached in the pool instead of returning it to the driver
-            cudaMemPool_t pool;
-            ISLE_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
-            uint64_t keep = UINT64_MAX;
-            ISLE_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        if (cudaHostAlloc((void **)&c.head_diag_host, 256, cudaHostAllocMapped) == cudaSuccess) {
+            std::memset(c.head_diag_host, 0, 256);
+            if (cudaHostGetDevicePointer((void **)&c.head_diag_dev, c.head_diag_host, 0) != cudaSuccess) c.head_diag_dev = nullptr;
+        } else {
+            cudaGetLastError();
+            c.head_diag_host = nullptr;
         }
         ISLE_CUBLAS_CHECK(cublasCreate(&c.cublas));
         ISLE_CUBLAS_CHECK(cublasSetStream(c.cublas, c.stream));
@@ -121,6 +140,7 @@ void isle_cuda_destroy(isle_cuda_ctx *h)
     Ctx &c = h->c;
     cudaSetDevice(c.device);
     tls_stream() = c.stream;
+    tls_cache() = &c.cache;
     if (c.stream) cudaStreamSynchronize(c.stream);
     for (auto &kv : c.stats)
         for (auto &ev : kv.second.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -131,6 +151,7 @@ void isle_cuda_destroy(isle_cuda_ctx *h)
     if (c.stream2) { cudaStreamSynchronize(c.stream2); cudaStreamDestroy(c.stream2); }
     if (c.ev_fork) cudaEventDestroy(c.ev_fork);
     if (c.ev_join) cudaEventDestroy(c.ev_join);
+    if (c.head_diag_host) cudaFreeHost(c.head_diag_host);
     if (c.cusolver) cusolverDnDestroy(c.cusolver);
     if (c.cublas) cublasDestroy(c.cublas);
     // device buffers are released by the DevBuf destructors inside Ctx
@@ -138,6 +159,7 @@ void isle_cuda_destroy(isle_cuda_ctx *h)
     delete h;
     if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     tls_stream() = nullptr;
+    tls_cache() = nullptr;
 }
 
 const char *isle_cuda_last_error(const isle_cuda_ctx *h) { return h ? h->c.last_error.c_str() : g_create_error.c_str(); }
@@ -292,6 +314,9 @@ int isle_cuda_get_stat(isle_cuda_ctx *h, const char *name, double *out)
         if (n == "launches") { *out = c.launches; return; }
         if (n == "nnz_B") { *out = (double)c.nnzB; return; }
         if (n == "D_B") { *out = (double)c.DB; return; }
+        if (n == "alloc_misses") { *out = c.cache.misses; return; }
+        if (n == "alloc_hits") { *out = c.cache.hits; return; }
+        if (n == "alloc_cached_bytes") { *out = (double)c.cache.cached_bytes; return; }
         if (n == "spmm_head_words") { *out = (double)c.H; return; }
         if (n == "spmm_tail_nnz") { *out = (double)c.nnz_tail; return; }
         auto ci = c.counters.find(n);
@@ -317,6 +342,7 @@ int isle_cuda_reset_stats(isle_cuda_ctx *h)
         drain(c);
         c.stats.clear();
         c.counters.clear();
+        c.cache.misses = c.cache.hits = 0.0;
         c.launches = 0.0;
     });
 }

@@ -58,40 +58,102 @@ struct Error : public std::runtime_error {
         if (!(cond)) throw ::isle::Error((code), std::string(msg));    \
     } while (0)
 
-// The stream device memory is allocated on / freed to: set by every C-ABI entry point to the
-// calling context's stream (one caller thread per context).  Allocation is
-// stream-ordered (cudaMallocAsync from the device's default pool with an unlimited release
-// threshold), so the per-call scratch buffers below cost no device synchronisation.
+// The stream the calling context works on: set by every C-ABI entry point (one caller thread per
+// context).
 inline cudaStream_t &tls_stream()
 {
     static thread_local cudaStream_t s = nullptr;
     return s;
 }
 
-// Owning device buffer (stream-ordered); movable, not copyable.
+// Per-context caching device allocator.  A step of the spectral core makes ~140 scratch allocations;
+// through cudaMallocAsync they cost 4-30 ms of host time per step on the bench box (measured: the
+// driver pool maps and unmaps physical memory behind them), which is as much as the whole operator.
+// Freed buffers are therefore kept in a size-ordered free list and handed out again (best fit within
+// 1/8 slack), so after the first step no allocation reaches the driver.  Reuse straight after a free
+// is safe because every kernel of a context is ordered on its one main stream (the second stream only
+// touches buffers that live as long as the operator layout).
+struct DevCache {
+    std::multimap<size_t, void *> free_;
+    size_t cached_bytes = 0;
+    double misses = 0.0, hits = 0.0;
+    static constexpr size_t kMaxCached = (size_t)48 << 30;
+
+    void *get(size_t bytes, size_t &cap)
+    {
+        auto it = free_.lower_bound(bytes);
+        if (it != free_.end() && it->first <= bytes + bytes / 8 + 4096) {
+            void *p = it->second;
+            cap = it->first;
+            cached_bytes -= cap;
+            free_.erase(it);
+            hits += 1.0;
+            return p;
+        }
+        misses += 1.0;
+        void *p = nullptr;
+        cap = (bytes + 511) & ~(size_t)511;
+        cudaError_t e = cudaMalloc(&p, cap);
+        if (e != cudaSuccess) {       // out of memory: drop the cache and retry once
+            cudaGetLastError();
+            trim();
+            e = cudaMalloc(&p, cap);
+        }
+        if (e != cudaSuccess)
+            throw Error(ISLE_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(cap) + "): " + cudaGetErrorString(e));
+        return p;
+    }
+    void put(void *p, size_t cap)
+    {
+        if (cached_bytes + cap > kMaxCached) trim();
+        free_.emplace(cap, p);
+        cached_bytes += cap;
+    }
+    void trim()
+    {
+        if (free_.empty()) return;
+        cudaDeviceSynchronize();
+        for (auto &kv : free_) cudaFree(kv.second);
+        free_.clear();
+        cached_bytes = 0;
+    }
+    ~DevCache() { trim(); }
+};
+
+inline DevCache *&tls_cache()
+{
+    static thread_local DevCache *c = nullptr;
+    return c;
+}
+
+// Owning device buffer served by the calling context's cache; movable, not copyable.
 template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
-    cudaStream_t s = nullptr;
+    size_t cap = 0;             // bytes actually owned
+    DevCache *owner = nullptr;
     DevBuf() = default;
     explicit DevBuf(size_t n_) { alloc(n_); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), cap(o.cap), owner(o.owner) { o.p = nullptr; o.n = 0; }
     DevBuf &operator=(DevBuf &&o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; owner = o.owner; o.p = nullptr; o.n = 0; }
         return *this;
     }
     ~DevBuf() { release(); }
     void alloc(size_t n_) {
         release();
         n = n_;
-        s = tls_stream();
-        if (n) ISLE_CUDA_CHECK(cudaMallocAsync((void **)&p, n * sizeof(T), s));
+        owner = tls_cache();
+        if (n) {
+            if (!owner) throw Error(ISLE_ERR_ARG, "device allocation outside a context call");
+            p = static_cast<T *>(owner->get(n * sizeof(T), cap));
+        }
     }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p && owner) owner->put(p, cap);
         p = nullptr;
         n = 0;
     }
@@ -117,6 +179,7 @@ struct WorkItem {          // one 4-lane group's share of a sparse pass
 };
 
 struct Ctx {
+    DevCache cache;            // declared first: destroyed after every DevBuf member below
     int device = 0;
     int rank = 0, world = 1;
     cudaStream_t stream = nullptr;
@@ -166,9 +229,11 @@ struct Ctx {
     DevBuf<int64_t> t1_off;                // [DB+1]
     DevBuf<uint32_t> t2_idx;               // rank-major tail: doc of each nonzero
     DevBuf<int64_t> t2_off;                // [V+1] (head ranks are empty rows)
+    DevBuf<uint32_t> colmax;               // per-column max |X| (bit patterns) for the exact power-of-two equilibration
     DevBuf<uint4> xbfp, ybfp;              // one-sector (32-byte) copies of the operand rows, two 16-byte units per row
     DevBuf<uint4> bits1, bits2;            // head bitmaps: (doc tile x rank chunk) and (rank tile x doc chunk)
     DevBuf<__nv_bfloat16> xsplit, ysplit;  // 3-piece bf16 splits of the head rows of Xs / of Y, K-major [N][Kpad]
+    uint32_t *head_diag_host = nullptr, *head_diag_dev = nullptr;   // host-mapped timeout record of the head kernel
     cudaStream_t stream2 = nullptr;        // head pass 2 runs beside the tail pass 2
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
@@ -246,7 +311,8 @@ void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z);
 int head_block_stride(int b);
 int head_split_rows(int b);
 void spmm_head_launch(Ctx &c, int b, const uint4 *bits, uint32_t num_mtiles, uint32_t NC, uint32_t nsplit,
-                      const __nv_bfloat16 *split, float *out, uint32_t m_valid, bool zero_out, cudaStream_t stream);
+                      const __nv_bfloat16 *split, float *out, uint32_t m_valid, bool zero_out, bool force_atomic,
+                      cudaStream_t stream);
 
 // ---- blockks.cu
 void block_ks(Ctx &c, uint64_t k, int b, int max_restarts, float tol, uint64_t seed,

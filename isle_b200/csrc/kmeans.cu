@@ -218,6 +218,53 @@ dist_simt_kernel(const float *__restrict__ P, const float *__restrict__ d2, uint
     }
 }
 
+// k-means++ refresh for a handful of new centers (1 + sqrt(s-5) per round, :2181-2199): one
+// HBM-bound pass over P.  The new centers sit in shared memory; a warp owns one document at a time,
+// lane l holds columns 4l + 128 i of the row, so the row is read once with coalesced float4 loads and
+// each center costs four FMAs per lane per 128 columns plus a shuffle reduction.
+// dist = ((-2 P_d . C_c) + ||C_c||^2) + ||P_d||^2, clamped at 0 (:2112-2126).
+static constexpr int kSkinnyMax = 16;
+
+__global__ void __launch_bounds__(256)
+pp_skinny_kernel(const float4 *__restrict__ P, const float *__restrict__ d2, uint32_t DB, uint32_t kp4,
+                 const float4 *__restrict__ C, const float *__restrict__ c2, uint32_t ncent, float *__restrict__ min_dist)
+{
+    extern __shared__ float4 sC[];     // [ncent][kp4]
+    for (uint32_t i = threadIdx.x; i < ncent * kp4; i += blockDim.x) sC[i] = C[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (; d < DB; d += nw) {
+        float acc[kSkinnyMax];
+#pragma unroll
+        for (int c = 0; c < kSkinnyMax; ++c) acc[c] = 0.f;
+        for (uint32_t col = lane; col < kp4; col += 32) {
+            const float4 p = __ldg(P + (size_t)d * kp4 + col);
+#pragma unroll
+            for (int c = 0; c < kSkinnyMax; ++c) {
+                if ((uint32_t)c < ncent) {
+                    const float4 q = sC[(size_t)c * kp4 + col];
+                    acc[c] = fmaf(p.x, q.x, fmaf(p.y, q.y, fmaf(p.z, q.z, fmaf(p.w, q.w, acc[c]))));
+                }
+            }
+        }
+        float best = FLT_MAX;
+        const float rd2 = d2[d];
+#pragma unroll
+        for (int c = 0; c < kSkinnyMax; ++c) {
+            if ((uint32_t)c < ncent) {
+                float v = acc[c];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                v = fmaxf(__fadd_rn(__fadd_rn(-2.0f * v, c2[c]), rd2), 0.0f);
+                best = fminf(best, v);
+            }
+        }
+        if (lane == 0) min_dist[d] = fminf(min_dist[d], best);
+    }
+}
+
 __global__ void row_l2_kernel(const float *__restrict__ C, uint32_t rows, uint32_t kp, float *__restrict__ out)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -240,9 +287,21 @@ static void distance_pass(Ctx &c, const float *C, const float *c2, uint32_t ncen
     // new centers) are a memory-bound pass over P and stay on the SIMT engine, which reads P once.
     const bool tc = c.opt("dist_kernel", 1) == 1 && dist_tc_supported(c, kp, ncent) &&
                     (mode == 0 || (int)ncent >= c.opt("dist_tc_min_centers", 32));
+    const size_t skinny_smem = (size_t)ncent * kp * sizeof(float);
+    const bool skinny = mode == 1 && !tc && ncent <= (uint32_t)kSkinnyMax && skinny_smem <= 160 * 1024 &&
+                        c.opt("pp_skinny", 1) != 0;
     // logical flops = 2 D_B ncent k
-    StatScope s(c, mode == 0 ? (tc ? "dist_tc" : "dist_simt") : (tc ? "pp_dist_tc" : "pp_dist_simt"),
+    StatScope s(c, mode == 0 ? (tc ? "dist_tc" : "dist_simt") : (tc ? "pp_dist_tc" : skinny ? "pp_dist_skinny" : "pp_dist_simt"),
                 (double)DB * kp * 4.0 + (double)DB * 8.0, 2.0 * (double)DB * ncent * (double)c.k);
+    if (skinny) {
+        ISLE_CUDA_CHECK(cudaFuncSetAttribute(pp_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skinny_smem));
+        const unsigned per_sm = skinny_smem > 100 * 1024 ? 1u : 2u;
+        pp_skinny_kernel<<<std::min<unsigned>((DB + 7) / 8, (unsigned)c.num_sms * per_sm * 4), 256, skinny_smem, c.stream>>>(
+            reinterpret_cast<const float4 *>(c.P.p), c.p_l2.p, DB, kp / 4, reinterpret_cast<const float4 *>(C), c2, ncent, min_dist);
+        ISLE_CUDA_CHECK(cudaGetLastError());
+        count_launch(c);
+        return;
+    }
     if (tc) {
         dist_tc_launch(c, C, c2, ncent, mode, assign, min_dist);
         return;
@@ -253,6 +312,12 @@ static void distance_pass(Ctx &c, const float *C, const float *c2, uint32_t ncen
     else
         dist_simt_kernel<1><<<grid, 256, 0, c.stream>>>(c.P.p, c.p_l2.p, DB, kp, C, c2, ncent, assign, min_dist);
     count_launch(c);
+}
+
+__global__ void iota_u32_kernel(uint32_t *__restrict__ p, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
 }
 
 // ------------------------------------------------------------------------------ Lloyd step
@@ -269,6 +334,59 @@ accumulate_kernel(const float4 *__restrict__ P, const uint32_t *__restrict__ ass
         for (uint32_t col = lane; col < kp4; col += 32)
             atomicAdd(sums + (size_t)cidx * kp4 + col, P[(size_t)d * kp4 + col]);
         if (lane == 0) atomicAdd(counts + cidx, 1u);
+    }
+}
+
+// Center sums over documents sorted by cluster: a warp walks a run of kSegDocs consecutive entries
+// of the sorted (cluster, doc) list, lane l accumulating float4 columns l, l+32, ... of the rows in
+// registers, and flushes with one vector atomic per lane only when the cluster changes or the run ends
+// (one flush per run instead of one per document).
+static constexpr uint32_t kSegDocs = 64;
+
+__global__ void __launch_bounds__(256)
+accumulate_sorted_kernel(const float4 *__restrict__ P, const uint32_t *__restrict__ sorted_cluster,
+                         const uint32_t *__restrict__ sorted_doc, uint32_t DB, uint32_t kp4, float4 *__restrict__ sums,
+                         uint32_t *__restrict__ counts)
+{
+    constexpr int kMaxCols = 4;    // float4 columns per lane handled in one sweep (kp <= 512 per sweep)
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nruns = (DB + kSegDocs - 1) / kSegDocs;
+    uint32_t run = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (; run < nruns; run += nw) {
+        const uint32_t i0 = run * kSegDocs, i1 = min(DB, i0 + kSegDocs);
+        for (uint32_t cbase = 0; cbase < kp4; cbase += 32 * kMaxCols) {
+            float4 acc[kMaxCols];
+#pragma unroll
+            for (int q = 0; q < kMaxCols; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t curc = sorted_cluster[i0], n = 0;
+            for (uint32_t i = i0; i <= i1; ++i) {
+                const uint32_t cl = i < i1 ? sorted_cluster[i] : 0xFFFFFFFFu;
+                if (cl != curc) {
+#pragma unroll
+                    for (int q = 0; q < kMaxCols; ++q) {
+                        const uint32_t col = cbase + q * 32 + lane;
+                        if (col < kp4) atomicAdd(sums + (size_t)curc * kp4 + col, acc[q]);
+                        acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (lane == 0 && cbase == 0) atomicAdd(counts + curc, n);
+                    curc = cl;
+                    n = 0;
+                }
+                if (i < i1) {
+                    const uint32_t d = sorted_doc[i];
+#pragma unroll
+                    for (int q = 0; q < kMaxCols; ++q) {
+                        const uint32_t col = cbase + q * 32 + lane;
+                        if (col < kp4) {
+                            const float4 v = __ldg(P + (size_t)d * kp4 + col);
+                            acc[q].x += v.x; acc[q].y += v.y; acc[q].z += v.z; acc[q].w += v.w;
+                        }
+                    }
+                    ++n;
+                }
+            }
+        }
     }
 }
 
@@ -358,6 +476,20 @@ void lloyd_projected(Ctx &c, uint64_t k64, float *centers_inout, int max_reps, u
     CentersDev cd(c, k, kp, centers_inout);
     DevBuf<uint32_t> a0(std::max<uint32_t>(DB, 1)), a1(std::max<uint32_t>(DB, 1)), counts(k), ndiff(1);
     DevBuf<float> sums((size_t)k * kp);
+    // documents sorted by cluster for the center sums (one radix pass over log2(k) bits per iteration)
+    const bool sorted_accum = c.opt("lloyd_sorted_accum", 1) != 0 && DB > 0;
+    DevBuf<uint32_t> doc_ids, skey, sdoc;
+    DevBuf<uint8_t> sort_tmp;
+    size_t sort_bytes = 0;
+    int key_bits = 1;
+    while ((1u << key_bits) < k) ++key_bits;
+    if (sorted_accum) {
+        doc_ids.alloc(DB); skey.alloc(DB); sdoc.alloc(DB);
+        iota_u32_kernel<<<grid_for(DB, 256), 256, 0, c.stream>>>(doc_ids.p, DB);
+        count_launch(c);
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, a0.p, skey.p, doc_ids.p, sdoc.p, (int)DB, 0, key_bits, c.stream);
+        sort_tmp.alloc(sort_bytes);
+    }
     uint32_t *cur = a0.p, *prev = a1.p;
     int iters = 0;
     for (int it = 0; it < max_reps; ++it) {
@@ -368,7 +500,14 @@ void lloyd_projected(Ctx &c, uint64_t k64, float *centers_inout, int max_reps, u
         ISLE_CUDA_CHECK(cudaMemsetAsync(counts.p, 0, counts.bytes(), c.stream));
         {
             StatScope s2(c, "lloyd_accum", (double)DB * kp * 4.0 + (double)DB * 4.0);
-            if (DB) {
+            if (sorted_accum) {
+                ISLE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sort_tmp.p, sort_bytes, cur, skey.p, doc_ids.p, sdoc.p, (int)DB, 0,
+                                                                key_bits, c.stream));
+                const uint32_t nruns = (DB + kSegDocs - 1) / kSegDocs;
+                accumulate_sorted_kernel<<<grid_for((size_t)nruns * 32, 256, c.num_sms * 8), 256, 0, c.stream>>>(
+                    reinterpret_cast<const float4 *>(c.P.p), skey.p, sdoc.p, DB, kp / 4, reinterpret_cast<float4 *>(sums.p), counts.p);
+                count_launch(c, 2);
+            } else if (DB) {
                 accumulate_kernel<<<grid_for((size_t)DB * 32, 256, c.num_sms * 8), 256, 0, c.stream>>>(
                     reinterpret_cast<const float4 *>(c.P.p), cur, DB, kp / 4, reinterpret_cast<float4 *>(sums.p), counts.p);
                 count_launch(c);

@@ -365,6 +365,7 @@ void build_csr(Ctx &c)
     c.ybuf.alloc((size_t)std::max<uint32_t>(c.DBpad, 1) * kStride);
     c.zbuf.alloc((size_t)V * kStride);
     c.xbfp.alloc((size_t)V * 2);
+    c.colmax.alloc(kStride);
     c.ybfp.alloc((size_t)std::max<uint32_t>(c.DBpad, 1) * 2);
     if (H) {
         const size_t nrows = 48;    // 3 bf16 pieces x up to 16 columns
@@ -532,14 +533,14 @@ spmm_gather_bfp_kernel(const WorkItem *__restrict__ items, size_t n_items, const
     if (sub >= 2) return;
     float *o = out + (size_t)it.out_row * kStride + 5 * u;
     const int ncol = min(5, b - 5 * u);
-    if (it.len & kSplitFlag) {
+    if (ADD || (it.len & kSplitFlag)) {     // ADD: the head engine may be adding into the same row right now
 #pragma unroll
         for (int k = 0; k < 5; ++k)
             if (k < ncol) atomicAdd(o + k, acc[k]);
     } else {
 #pragma unroll
         for (int k = 0; k < 5; ++k)
-            if (k < ncol) o[k] = ADD ? o[k] + acc[k] : acc[k];
+            if (k < ncol) o[k] = acc[k];
     }
 }
 
@@ -552,12 +553,45 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16 &h, __nv_bfloat16 
     l = __float2bfloat16_rn(r2);
 }
 
+// colmax_bits[j] = bit pattern of max_w |X[w + j ld]| (non-negative floats order like unsigned integers)
+__global__ void __launch_bounds__(256)
+colmax_kernel(const float *__restrict__ X, size_t ld, uint32_t n, int b, uint32_t *__restrict__ colmax_bits)
+{
+    float m[kStride];
+#pragma unroll
+    for (int j = 0; j < kStride; ++j) m[j] = 0.f;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int j = 0; j < kStride; ++j)
+            if (j < b) m[j] = fmaxf(m[j], fabsf(X[w + (size_t)j * ld]));
+    }
+#pragma unroll
+    for (int j = 0; j < kStride; ++j) {
+        if (j < b) {
+            float v = m[j];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if ((threadIdx.x & 31) == 0 && v > 0.f) atomicMax(colmax_bits + j, __float_as_uint(v));
+        }
+    }
+}
+
+// Exact power-of-two column equilibration for the block-FP rows: columns that share a unit get the same
+// magnitude, so the shared exponent costs no precision whatever the scales of the caller's columns are.
+// down = 2^-e, up = 2^e with 2^e <= colmax < 2^(e+1); 1 when the column is zero / not finite.
+__device__ __forceinline__ float col_pow2(uint32_t colmax_bits, bool up)
+{
+    const uint32_t E = (colmax_bits >> 23) & 0xFFu;
+    if (E == 0 || E >= 254) return 1.0f;
+    return __uint_as_float((up ? E : 254u - E) << 23);
+}
+
 // Rank space: Xs[r, j] = sqrt_zeta[w] * X[w + j ld], w = word_of_rank[r]  (j < b), zero padded to 16
 // floats; head ranks are also written as three bf16 pieces, K-major: xsplit[(piece*BS + j) * H + r].
 __global__ void __launch_bounds__(256)
 pack_scaled_kernel(const float *__restrict__ X, size_t ld, uint32_t n, int b, const float *__restrict__ scale,
                    const uint32_t *__restrict__ word_of_rank, float4 *__restrict__ out, uint4 *__restrict__ out_bfp,
-                   uint32_t H, int BS, __nv_bfloat16 *__restrict__ xsplit)
+                   const uint32_t *__restrict__ colmax_bits, uint32_t H, int BS, __nv_bfloat16 *__restrict__ xsplit)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
@@ -565,7 +599,8 @@ pack_scaled_kernel(const float *__restrict__ X, size_t ld, uint32_t n, int b, co
     const float s = scale ? scale[w] : 1.0f;
     float v[kStride];
 #pragma unroll
-    for (int j = 0; j < kStride; ++j) v[j] = (j < b) ? s * X[w + (size_t)j * ld] : 0.0f;
+    for (int j = 0; j < kStride; ++j)
+        v[j] = (j < b) ? s * (X[w + (size_t)j * ld] * (colmax_bits ? col_pow2(colmax_bits[j], false) : 1.0f)) : 0.0f;
     if (out_bfp) {      // b <= 10: one-sector rows
         out_bfp[(size_t)r * 2] = bfp_encode5(v);
         out_bfp[(size_t)r * 2 + 1] = bfp_encode5(v + 5);
@@ -622,7 +657,7 @@ ysplit_kernel(const float4 *__restrict__ Y, uint32_t DB, uint32_t DBpad, int b, 
 // Z[w + j ld] = sqrt_zeta[w] * T[rank_of[w], j]
 __global__ void __launch_bounds__(256)
 unpack_scaled_kernel(const float *__restrict__ T, uint32_t n, int b, const float *__restrict__ scale,
-                     const uint32_t *__restrict__ rank_of, float *__restrict__ Z, size_t ld)
+                     const uint32_t *__restrict__ rank_of, const uint32_t *__restrict__ colmax_bits, float *__restrict__ Z, size_t ld)
 {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n) return;
@@ -636,7 +671,7 @@ unpack_scaled_kernel(const float *__restrict__ T, uint32_t n, int b, const float
     }
 #pragma unroll
     for (int j = 0; j < kStride; ++j)
-        if (j < b) Z[w + (size_t)j * ld] = s * v[j];
+        if (j < b) Z[w + (size_t)j * ld] = (s * v[j]) * (colmax_bits ? col_pow2(colmax_bits[j], true) : 1.0f);
 }
 
 static void launch_gather(Ctx &c, int nch, bool add, const WorkItem *items, size_t n_items, const uint32_t *idx,
@@ -685,9 +720,14 @@ void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z)
 
     // block sizes <= 10 gather one-sector (32-byte) operand rows; wider blocks use padded fp32 rows
     const bool bfp = b <= 10 && c.opt("spmm_bfp", 1) != 0;
+    if (bfp) {
+        ISLE_CUDA_CHECK(cudaMemsetAsync(c.colmax.p, 0, c.colmax.bytes(), c.stream));
+        colmax_kernel<<<std::min<unsigned>((V + 255) / 256, (unsigned)c.num_sms * 2), 256, 0, c.stream>>>(X, (size_t)V, V, b, c.colmax.p);
+        count_launch(c);
+    }
     pack_scaled_kernel<<<(V + 255) / 256, 256, 0, c.stream>>>(X, (size_t)V, V, b, c.sqrt_zeta.p, c.word_of_rank.p,
-                                                               reinterpret_cast<float4 *>(c.xs.p), bfp ? c.xbfp.p : nullptr, H, BS,
-                                                               c.xsplit.p);
+                                                               reinterpret_cast<float4 *>(c.xs.p), bfp ? c.xbfp.p : nullptr,
+                                                               bfp ? c.colmax.p : nullptr, H, BS, c.xsplit.p);
     count_launch(c);
     // T is always zeroed: word rows are split routinely and the head adds partial sums atomically.
     ISLE_CUDA_CHECK(cudaMemsetAsync(c.zbuf.p, 0, c.zbuf.bytes(), c.stream));
@@ -695,11 +735,20 @@ void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z)
         // bytes_pass = nnz*4 + (rows+1)*8 + dense_in*4 + dense_out*4
         StatScope s(c, "spmm_bt", (double)c.nnzB * 4.0 + ((double)DB + 1) * 8.0 + ((double)V + DB) * b * 4.0,
                     2.0 * c.nnzB * b);
-        if (H) {
+        if (H && bfp && c.opt("spmm_fork", 1) != 0) {
+            // head and tail add into a zeroed Y side by side (tensor pipe + ALU vs L1TEX-bound gathers)
+            ISLE_CUDA_CHECK(cudaMemsetAsync(c.ybuf.p, 0, c.ybuf.bytes(), c.stream));
+            ISLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
+            ISLE_CUDA_CHECK(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
+            spmm_head_launch(c, b, c.bits1.p, c.DBpad / kHeadTile, H / kHeadChunk, 1, c.xsplit.p, c.ybuf.p, DB, false, true, c.stream2);
+            ISLE_CUDA_CHECK(cudaEventRecord(c.ev_join, c.stream2));
+            launch_gather_bfp(c, b, true, c.items_bt.p, c.n_items_bt, c.t1_idx.p, c.xbfp.p, c.ybuf.p);
+            ISLE_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
+        } else if (H) {
             {
                 StatScope sh(c, "spmm_head1");
                 // every row of Y is written (store mode): Y = head part
-                spmm_head_launch(c, b, c.bits1.p, c.DBpad / kHeadTile, H / kHeadChunk, 1, c.xsplit.p, c.ybuf.p, DB, true, c.stream);
+                spmm_head_launch(c, b, c.bits1.p, c.DBpad / kHeadTile, H / kHeadChunk, 1, c.xsplit.p, c.ybuf.p, DB, true, false, c.stream);
             }
             StatScope st(c, "spmm_tail1");
             if (bfp) launch_gather_bfp(c, b, true, c.items_bt.p, c.n_items_bt, c.t1_idx.p, c.xbfp.p, c.ybuf.p);
@@ -727,7 +776,7 @@ void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z)
                 // the head and the tail of pass 2 write disjoint rows of T: run them side by side
                 ISLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
                 ISLE_CUDA_CHECK(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
-                spmm_head_launch(c, b, c.bits2.p, mt, NC2, nsplit, c.ysplit.p, c.zbuf.p, H, false, c.stream2);
+                spmm_head_launch(c, b, c.bits2.p, mt, NC2, nsplit, c.ysplit.p, c.zbuf.p, H, false, false, c.stream2);
                 ISLE_CUDA_CHECK(cudaEventRecord(c.ev_join, c.stream2));
                 if (bfp) launch_gather_bfp(c, b, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybfp.p, c.zbuf.p);
                 else launch_gather(c, nch, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybuf.p, c.zbuf.p);
@@ -735,7 +784,7 @@ void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z)
             } else {
                 {
                     StatScope sh(c, "spmm_head2");
-                    spmm_head_launch(c, b, c.bits2.p, mt, NC2, nsplit, c.ysplit.p, c.zbuf.p, H, false, c.stream);
+                    spmm_head_launch(c, b, c.bits2.p, mt, NC2, nsplit, c.ysplit.p, c.zbuf.p, H, false, false, c.stream);
                 }
                 StatScope st(c, "spmm_tail2");
                 if (bfp) launch_gather_bfp(c, b, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybfp.p, c.zbuf.p);
@@ -746,7 +795,8 @@ void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z)
             else launch_gather(c, nch, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybuf.p, c.zbuf.p);
         }
     }
-    unpack_scaled_kernel<<<(V + 255) / 256, 256, 0, c.stream>>>(c.zbuf.p, V, b, c.sqrt_zeta.p, c.rank_of.p, Z, (size_t)V);
+    unpack_scaled_kernel<<<(V + 255) / 256, 256, 0, c.stream>>>(c.zbuf.p, V, b, c.sqrt_zeta.p, c.rank_of.p,
+                                                                 bfp ? c.colmax.p : nullptr, Z, (size_t)V);
     count_launch(c);
     if (c.world > 1) {
         // doc-sharded: Z = sum over ranks of B_g (B_g^T X)   

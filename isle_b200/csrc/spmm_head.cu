@@ -34,8 +34,8 @@ namespace {
 constexpr uint32_t kGroups = 4;          // worker groups = A stages in TMEM
 constexpr uint32_t kWarpMma = 4 * kGroups, kWarpTma = 4 * kGroups + 1;
 constexpr int kThreads = 32 * (4 * kGroups + 2);
-constexpr uint32_t kTmemCols = 512;      // accumulators (<= 48 cols) at +0 and +64, four A stages of 64 cols at +128
-constexpr uint32_t kTmemA = 128;
+constexpr uint32_t kTmemCols = 512;      // four accumulators (<= 48 cols, stride 64) at +0, four A stages of 64 cols at +256
+constexpr uint32_t kTmemA = 256;
 constexpr uint32_t kBitBytes = kHeadTile * 16;   // 128 rows x 128 bits
 
 // ---------------------------------------------------------------------------------- PTX
@@ -52,13 +52,35 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+// Bounded waits: a protocol bug records where it stopped (role / barrier / job / chunk, first writer wins)
+// in host-mapped memory and traps, so the launch fails with a diagnosable error instead of hanging.
+__device__ uint32_t *g_head_diag = nullptr;
+constexpr uint32_t kSpinLimit = 1u << 17;
+
+__device__ __noinline__ void head_timeout(uint32_t code, uint32_t a, uint32_t b)
+{
+    // one record per waiter class (code low byte: 0x10 TMA, 0x20/0x21 MMA, 0x30/0x31 + group workers)
+    uint32_t *d = g_head_diag;
+    if (d) {
+        const uint32_t cls = code & 0xFFu;
+        const uint32_t slot = cls == 0x10 ? 0 : cls == 0x20 ? 1 : cls == 0x21 ? 2 : (cls & 0xF0u) == 0x30 ? 3 + (cls & 7u) : 11;
+        uint32_t *r = d + slot * 5;
+        if (atomicCAS_system(r, 0u, 1u + code) == 0u) {
+            r[1] = blockIdx.x; r[2] = threadIdx.x; r[3] = a; r[4] = b;
+        }
+        __threadfence_system();
+        // give the other stuck roles of this CTA time to leave their records before the context dies
+        for (int i = 0; i < 4000; ++i) __nanosleep(1000);
+    }
+    __trap();
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t code = 0, uint32_t da = 0, uint32_t db = 0)
 {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
 #pragma unroll 1
-    for (uint32_t spins = 0; spins < (1u << 23); ++spins) {
+    for (uint32_t spins = 0; spins < kSpinLimit; ++spins) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
@@ -70,29 +92,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "memory");
         if (done) return;
     }
-    __trap();
+    head_timeout(code, da, db);
 }
 // Waits for two barriers; the two try_waits are issued back to back so their latencies overlap.
-__device__ __forceinline__ void mbar_wait2(uint64_t *bar_a, uint32_t parity_a, uint64_t *bar_b, uint32_t parity_b)
+__device__ __forceinline__ void mbar_wait2(uint64_t *bar_a, uint32_t parity_a, uint64_t *bar_b, uint32_t parity_b,
+                                           uint32_t code = 0, uint32_t da = 0, uint32_t db = 0)
 {
     const uint32_t addr_a = smem_u32(bar_a), addr_b = smem_u32(bar_b);
     uint32_t done = 0;
+    uint32_t pa = 0;
 #pragma unroll 1
-    for (uint32_t spins = 0; spins < (1u << 23); ++spins) {
+    for (uint32_t spins = 0; spins < kSpinLimit; ++spins) {
         asm volatile(
             "{\n\t"
             ".reg .pred p, q;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5;\n\t"
+            "selp.u32 %1, 1, 0, p;\n\t"
             "and.pred p, p, q;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}"
-            : "=r"(done)
+            : "=r"(done), "=r"(pa)
             : "r"(addr_a), "r"(parity_a), "r"(addr_b), "r"(parity_b)
             : "memory");
         if (done) return;
     }
-    __trap();
+    head_timeout(code + (pa ? 0x100u : 0u), da, db);     // +0x100: the first barrier had completed
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
 {
@@ -202,8 +227,11 @@ struct HeadParams {
 
 // The tensor core adds into its fp32 accumulator with truncation, so the rounding error of a long
 // accumulation chain grows linearly.  A job's K range is therefore cut into segments of p.seg chunks
-// (8 MMAs each); segments alternate between two TMEM accumulators and each one is drained (tcgen05.ld,
-// three-piece sum, atomic add or store) by one worker group while the next is being multiplied.
+// (8 MMAs each); segment n accumulates in TMEM accumulator n mod 4 and is drained (tcgen05.ld, three-piece
+// sum, atomic add or store) by worker group n mod 4 while the next segments are being multiplied.  Each
+// accumulator's full/empty barrier pair therefore has exactly one waiter on each side, observing every phase
+// in order -- a parity wait cannot tell "phase n done" from "phase n-2 done", so a shared pair would let a
+// group that ran two short segments ahead of the tensor core see its wait satisfied early.
 //
 // Workers: 16 warps = 4 groups x 4 lane quarters.  Group g expands the chunks whose running index is
 // g mod 4 into its own A stage (TMEM columns 128 + 64 g), so four chunks are in flight and the
@@ -224,17 +252,19 @@ spmm_head_kernel(const __grid_constant__ CUtensorMap map_b, const HeadParams p)
     uint64_t *empty = full + p.stages;                      // [stages]  MMA done + the group's 4 warps have read the bits
     uint64_t *a_full = empty + p.stages;                    // [4]       group stored its A stage
     uint64_t *a_empty = a_full + kGroups;                   // [4]       MMAs reading the A stage retired
-    uint64_t *acc_full = a_empty + kGroups;                 // [2]       segment accumulated
-    uint64_t *acc_empty = acc_full + 2;                     // [2]       a group drained the accumulator
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    uint64_t *acc_full = a_empty + kGroups;                 // [4]       segment accumulated
+    uint64_t *acc_empty = acc_full + kGroups;               // [4]       its group drained the accumulator
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + kGroups);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t njobs = p.num_mtiles * p.nsplit;
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 5); }
-        for (uint32_t a = 0; a < kGroups; ++a) { mbar_init(&a_full[a], 4); mbar_init(&a_empty[a], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        for (uint32_t a = 0; a < kGroups; ++a) {
+            mbar_init(&a_full[a], 4); mbar_init(&a_empty[a], 1);
+            mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     }
@@ -256,7 +286,7 @@ spmm_head_kernel(const __grid_constant__ CUtensorMap map_b, const HeadParams p)
                 const uint32_t c0 = (uint32_t)((uint64_t)p.NC * part / p.nsplit);
                 const uint32_t c1 = (uint32_t)((uint64_t)p.NC * (part + 1) / p.nsplit);
                 for (uint32_t ch = c0; ch < c1; ++ch) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_wait(&empty[stage], phase ^ 1, 0x10, job, ch);
                     uint8_t *st = smem + (size_t)stage * stage_bytes;
                     mbar_expect_tx(&full[stage], stage_bytes);
                     tma_load_2d(st, &map_b, &full[stage], (int)(ch * kHeadChunk), 0);
@@ -280,10 +310,10 @@ spmm_head_kernel(const __grid_constant__ CUtensorMap map_b, const HeadParams p)
                 const uint32_t c1 = (uint32_t)((uint64_t)p.NC * (part + 1) / p.nsplit);
                 for (uint32_t s0 = c0; s0 < c1; s0 += p.seg) {
                     const uint32_t s1 = min(c1, s0 + p.seg);
-                    mbar_wait(&acc_empty[buf], bphase ^ 1);
+                    mbar_wait(&acc_empty[buf], bphase ^ 1, 0x20, job, s0);
                     const uint32_t d_tmem = tmem_base + buf * 64;
                     for (uint32_t ch = s0; ch < s1; ++ch) {
-                        mbar_wait2(&full[stage], phase, &a_full[g], gphase);
+                        mbar_wait2(&full[stage], phase, &a_full[g], gphase, 0x21, job, ch);
                         tc_fence_after();
                         const uint64_t bd = desc0 + (uint64_t)(stage * (stage_bytes >> 4));
                         const uint32_t a_tmem = tmem_base + kTmemA + g * 64;
@@ -301,8 +331,7 @@ spmm_head_kernel(const __grid_constant__ CUtensorMap map_b, const HeadParams p)
                         if (++g == kGroups) { g = 0; gphase ^= 1; }
                     }
                     umma_commit(&acc_full[buf], 1u);
-                    buf ^= 1;
-                    if (buf == 0) bphase ^= 1;
+                    if (++buf == kGroups) { buf = 0; bphase ^= 1; }
                 }
             }
         }
@@ -311,13 +340,13 @@ spmm_head_kernel(const __grid_constant__ CUtensorMap map_b, const HeadParams p)
         const uint32_t grp = warp >> 2, quarter = warp & 3;
         const uint32_t trow = quarter * 32 + lane;
         const uint32_t lane_base = (quarter * 32u) << 16;
-        uint32_t stage = 0, phase = 0, g = 0, gphase = 0, buf = 0, bphase = 0, sg = 0;
+        uint32_t stage = 0, phase = 0, g = 0, gphase = 0, buf = 0, bphase = 0;
         // the segment this group has to drain: accumulator, barrier phase, output row, store/add
         bool pend = false;
         uint32_t pend_buf = 0, pend_phase = 0, pend_row = 0;
 
         auto drain = [&]() {
-            mbar_wait(&acc_full[pend_buf], pend_phase);
+            mbar_wait(&acc_full[pend_buf], pend_phase, 0x30 + grp, pend_row, pend_buf * 2 + pend_phase);
             tc_fence_after();
             uint32_t acc[N];
 #pragma unroll
@@ -353,7 +382,7 @@ spmm_head_kernel(const __grid_constant__ CUtensorMap map_b, const HeadParams p)
                 const uint32_t s1 = min(c1, s0 + p.seg);
                 for (uint32_t ch = s0; ch < s1; ++ch) {
                     if (g == grp) {
-                        mbar_wait2(&full[stage], phase, &a_empty[grp], gphase ^ 1);
+                        mbar_wait2(&full[stage], phase, &a_empty[grp], gphase ^ 1, 0x34 + grp, job, ch);
                         const uint4 m = reinterpret_cast<const uint4 *>(smem + (size_t)stage * stage_bytes + 2 * sub_bytes)[trow];
                         tc_fence_after();
                         const uint32_t a_addr = tmem_base + lane_base + kTmemA + grp * 64;
@@ -374,16 +403,14 @@ spmm_head_kernel(const __grid_constant__ CUtensorMap map_b, const HeadParams p)
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     if (++g == kGroups) { g = 0; gphase ^= 1; }
                 }
-                if (sg == grp) {
+                if (buf == grp) {      // segment n uses accumulator n mod 4 and is drained by group n mod 4
                     if (pend) drain();
                     pend = true;
                     pend_buf = buf;
                     pend_phase = bphase;
                     pend_row = mtile * kHeadTile + trow;
                 }
-                if (++sg == kGroups) sg = 0;
-                buf ^= 1;
-                if (buf == 0) bphase ^= 1;
+                if (++buf == kGroups) { buf = 0; bphase ^= 1; }
             }
         }
         if (pend) drain();
@@ -437,6 +464,13 @@ void launch_head_t(Ctx &c, const __nv_bfloat16 *split, uint64_t kpad, const Head
     p.stages = (uint32_t)std::max(2, std::min(16, c.opt("spmm_head_stages", 12)));
     const uint32_t smem_bytes = p.stages * stage_bytes + 1024 + 512;
     ISLE_CUDA_CHECK(cudaFuncSetAttribute(spmm_head_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    if (c.head_diag_dev) {
+        static uint32_t *installed = nullptr;     // device-side symbol, set once per process and pointer
+        if (installed != c.head_diag_dev) {
+            ISLE_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_head_diag, &c.head_diag_dev, sizeof(uint32_t *), 0, cudaMemcpyHostToDevice, stream));
+            installed = c.head_diag_dev;
+        }
+    }
     const CUtensorMap map = make_split_map(split, N, kpad);
     const uint32_t njobs = p.num_mtiles * p.nsplit;
     const unsigned grid = std::min<uint32_t>(njobs, (uint32_t)c.num_sms);
@@ -453,7 +487,8 @@ int head_split_rows(int b) { return (3 * head_block_stride(b) + 15) / 16 * 16; }
 // out[m, 0:b] (+)= sum_k bit(m, k) * In[k, 0:b], In given as its 3-piece bf16 split [N][kpad].
 // zero_out: `out` (num_mtiles * 128 rows) is cleared first when partial sums are added atomically.
 void spmm_head_launch(Ctx &c, int b, const uint4 *bits, uint32_t num_mtiles, uint32_t NC, uint32_t nsplit,
-                      const __nv_bfloat16 *split, float *out, uint32_t m_valid, bool zero_out, cudaStream_t stream)
+                      const __nv_bfloat16 *split, float *out, uint32_t m_valid, bool zero_out, bool force_atomic,
+                      cudaStream_t stream)
 {
     if (!num_mtiles || !NC) return;
     HeadParams p;
@@ -462,7 +497,7 @@ void spmm_head_launch(Ctx &c, int b, const uint4 *bits, uint32_t num_mtiles, uin
     p.stages = 0;
     p.seg = (uint32_t)std::max(1, c.opt("spmm_head_seg", 16));
     // rows receive several partial sums (K split over jobs or segments): added into a zeroed output
-    p.atomic = (p.nsplit > 1 || NC > p.seg) ? 1u : 0u;
+    p.atomic = (p.nsplit > 1 || NC > p.seg || force_atomic) ? 1u : 0u;
     if (p.atomic && zero_out) ISLE_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)num_mtiles * kHeadTile * 16 * sizeof(float), stream));
     const uint64_t kpad = (uint64_t)NC * kHeadChunk;
     switch (head_block_stride(b)) {

@@ -155,6 +155,48 @@ def test_spsptr_multiply_c1_split_rows(ctx, golden_c1, corpus_c1):
     assert np.max(np.abs(Z2 - (2 * Z + Z1))) <= 1e-4 * np.max(np.abs(Z2))
 
 
+# every engine combination of the operator must give the same product: dense head on tcgen05 vs index
+# lists only, one-sector (block floating point) operand rows vs padded fp32 rows, forked vs serial streams
+ENGINE_OPTS = [
+    dict(spmm_head=0, spmm_bfp=0, spmm_fork=0),
+    dict(spmm_head=0, spmm_bfp=1, spmm_fork=0),
+    dict(spmm_head=1, spmm_bfp=0, spmm_fork=0),
+    dict(spmm_head=1, spmm_bfp=1, spmm_fork=0),
+    dict(spmm_head=1, spmm_bfp=1, spmm_fork=1),
+    dict(spmm_head=1, spmm_bfp=1, spmm_fork=1, spmm_head_density_ppm=60000, spmm_head_seg=1),
+    dict(spmm_head=1, spmm_bfp=1, spmm_fork=1, spmm_head_density_ppm=1000, spmm_head_max=4096, spmm_head_seg=2),
+]
+ENGINE_DEFAULTS = dict(spmm_head=1, spmm_bfp=1, spmm_fork=1, spmm_head_density_ppm=12000, spmm_head_max=4096,
+                       spmm_head_seg=16)
+
+
+@pytest.mark.parametrize("opts", ENGINE_OPTS, ids=lambda o: "-".join(f"{k[5:]}{v}" for k, v in o.items()))
+@pytest.mark.parametrize("b", [3, 10, 16])
+def test_spsptr_engines_agree(ctx, golden_c1, corpus_c1, opts, b):
+    g, c = golden_c1, corpus_c1
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    bv, br, bo, _ = O.threshold_and_copy(vals, c.rows, c.offsets, g["zetas"])
+    Bo = O.to_csc(bv, br, bo, c.V)
+    X = np.random.default_rng(7 + b).standard_normal((c.V, b)).astype(np.float32)
+    X[:, 0] *= 1e-3                      # columns of very different scale share a block-FP unit
+    X[::7, :] = 0.0                      # all-zero operand rows
+    Zr = (Bo @ (Bo.T @ X.astype(np.float64)))
+    try:
+        for k_, v_ in {**ENGINE_DEFAULTS, **opts}.items():
+            ctx.set_option(k_, v_)
+        A, B, zetas, nn, oc = make_AB(ctx, c.V, c.D, c.k, vals, c.rows, c.offsets, avg, nz)
+        Z = B.multiply(X)
+        H = int(ctx.stat("spmm_head_words"))
+        assert (H > 0) == bool(opts["spmm_head"])
+        if opts.get("spmm_head_density_ppm") == 1000:
+            assert H >= 1024             # K split into many segments, partial sums added atomically
+        col_scale = np.max(np.abs(Zr), axis=0)
+        assert np.max(np.abs(Z - Zr) / col_scale) <= 3e-6
+    finally:
+        for k_, v_ in ENGINE_DEFAULTS.items():
+            ctx.set_option(k_, v_)
+
+
 # ---------------------------------------------------------------- stage C: eigenpairs
 def check_eigs(ev, U, ev_ref, U_ref, frob):
     k = len(ev)

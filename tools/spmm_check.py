@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--density-ppm", type=int, nargs="*", default=[12000])
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--seg", type=int, nargs="*", default=[16])
     ap.add_argument("--only-head-serial", action="store_true")
     a = ap.parse_args()
 
@@ -90,15 +91,16 @@ def main():
     if not a.only_head_serial:
         ctx.set_option("spmm_head", 0)
         run("gather only", a.reps)
-    for ppm in a.density_ppm:
+    for ppm, seg in [(p_, s_) for p_ in a.density_ppm for s_ in a.seg]:
+        ctx.set_option("spmm_head_seg", seg)
         ctx.set_option("spmm_head", 1)
         ctx.set_option("spmm_head_density_ppm", ppm)
         ctx.set_option("spmm_fork", 0)
-        run(f"head {ppm}ppm serial", a.reps)
+        run(f"head {ppm}ppm seg{seg} serial", a.reps)
         if a.only_head_serial:
             continue
         ctx.set_option("spmm_fork", 1)
-        run(f"head {ppm}ppm fork", a.reps)
+        run(f"head {ppm}ppm seg{seg} fork", a.reps)
     ctx.close()
 
 
