@@ -296,42 +296,54 @@ __device__ __forceinline__ void gram_partial(const CholQrParams &p, const double
 __device__ __forceinline__ bool chol_and_invert(const double *part, int b, double *G, double (*R)[kMaxB],
                                                 double (*Rinv)[kMaxB], int *s_ok, bool apply_rank_cut)
 {
-    {
+    {   // fixed-order sum; the loads are independent of the running sum, so unrolling keeps eight in flight
         double v = 0.0;
-        for (unsigned blk = 0; blk < gridDim.x; ++blk) v += part[(size_t)blk * 256 + threadIdx.x];
+        const unsigned nb = gridDim.x;
+        unsigned blk = 0;
+        for (; blk + 8 <= nb; blk += 8) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = part[(size_t)(blk + u) * 256 + threadIdx.x];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v += t[u];
+        }
+        for (; blk < nb; ++blk) v += part[(size_t)blk * 256 + threadIdx.x];
         G[threadIdx.x] = v;
+        R[threadIdx.x >> 4][threadIdx.x & 15] = 0.0;
+        Rinv[threadIdx.x >> 4][threadIdx.x & 15] = 0.0;
+        if (threadIdx.x == 0) *s_ok = 1;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        bool ok = true;
-        for (int i = 0; i < kMaxB; ++i)
-            for (int j = 0; j < kMaxB; ++j) { R[i][j] = 0.0; Rinv[i][j] = 0.0; }
-        for (int j = 0; j < b && ok; ++j) {
-            const double gjj = G[j * 16 + j];
-            double d = gjj;
+    // right-looking Cholesky on the first warp: lane c owns column c of the upper factor
+    if (threadIdx.x < 32) {
+        const int c = threadIdx.x;
+        for (int j = 0; j < b; ++j) {
+            double d = G[j * 16 + j];
             for (int i = 0; i < j; ++i) d -= R[i][j] * R[i][j];
             // reference rank cut: ||a_j - proj||_2 < 1e-6 (ks_utils.h:69); Gram noise floor ~ 1e-9 G_jj
-            const double floor_ = apply_rank_cut ? fmax(1e-12, 1e-9 * gjj) : 0.0;
-            if (!(d > floor_)) { ok = false; break; }
+            const double floor_ = apply_rank_cut ? fmax(1e-12, 1e-9 * G[j * 16 + j]) : 0.0;
+            if (!(d > floor_)) {            // uniform across the warp: every lane evaluates the same pivot
+                if (c == 0) *s_ok = 0;
+                break;
+            }
             const double rjj = sqrt(d);
-            R[j][j] = rjj;
-            for (int c = j + 1; c < b; ++c) {
+            if (c == j) R[j][j] = rjj;
+            if (c > j && c < b) {
                 double t = G[j * 16 + c];
                 for (int i = 0; i < j; ++i) t -= R[i][j] * R[i][c];
                 R[j][c] = t / rjj;
             }
+            __syncwarp();
         }
-        if (ok) {   // upper-triangular inverse by back substitution, column by column
-            for (int c = 0; c < b; ++c) {
-                Rinv[c][c] = 1.0 / R[c][c];
-                for (int i = c - 1; i >= 0; --i) {
-                    double t = 0.0;
-                    for (int l = i + 1; l <= c; ++l) t += R[i][l] * Rinv[l][c];
-                    Rinv[i][c] = -t / R[i][i];
-                }
+        __syncwarp();
+        if (*s_ok && c < b) {   // column c of the upper-triangular inverse by back substitution
+            Rinv[c][c] = 1.0 / R[c][c];
+            for (int i = c - 1; i >= 0; --i) {
+                double t = 0.0;
+                for (int l = i + 1; l <= c; ++l) t += R[i][l] * Rinv[l][c];
+                Rinv[i][c] = -t / R[i][i];
             }
         }
-        *s_ok = ok ? 1 : 0;
     }
     __syncthreads();
     return *s_ok != 0;
@@ -391,7 +403,7 @@ cholqr2_kernel(CholQrParams p)
 // N = b <= 16, for which a library GEMM spends its time in split-K bookkeeping.
 //   wtf:   C = W^T F   per-chunk partials (fixed order -> deterministic) + ordered reduce
 //   fsub:  F -= W C,   one thread per row of F, C staged in shared memory
-static constexpr int kWtfChunk = 1024;   // rows of W per CTA
+static constexpr int kWtfChunk = 512;    // rows of W per CTA (its F slice is staged in shared memory)
 static constexpr int kWtfCols = 32;      // columns of W per CTA (4 per warp)
 
 template <int BP>
@@ -399,30 +411,45 @@ __global__ void __launch_bounds__(256, 2)
 wtf_partial_kernel(const float *__restrict__ W, const float *__restrict__ F, int64_t n, int rows, int b,
                    float *__restrict__ partial /* [chunks][rows][BP] */)
 {
+    // the CTA's slice of F sits in shared memory ([column][row]: lanes read consecutive words), so the inner
+    // loop issues only the W loads: four columns x four 32-row slabs = 16 independent loads per lane in flight
+    __shared__ float sF[BP][kWtfChunk];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i0 = (int64_t)blockIdx.y * kWtfChunk;
+    for (int t = threadIdx.x; t < BP * kWtfChunk; t += 256) {
+        const int c = t / kWtfChunk, r = t % kWtfChunk;
+        sF[c][r] = (c < b && i0 + r < n) ? F[i0 + r + (size_t)c * n] : 0.f;
+    }
+    __syncthreads();
     const int j0 = blockIdx.x * kWtfCols + warp * 4;
     if (j0 >= rows) return;
-    const int64_t i0 = (int64_t)blockIdx.y * kWtfChunk;
     float acc[4][BP];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
         for (int c = 0; c < BP; ++c) acc[jj][c] = 0.f;
     const int nj = min(4, rows - j0);
-    // all loads of an iteration are issued before the first FMA; 16 iterations per CTA
+    const float *wp[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) wp[jj] = W + (size_t)(j0 + min(jj, nj - 1)) * n;   // clamp: unused columns re-read a valid one
 #pragma unroll 1
-    for (int it = 0; it < kWtfChunk / 32; ++it) {
-        const int64_t i = i0 + it * 32 + lane;
-        if (i < n) {
-            float f[BP], w[4];
+    for (int it = 0; it < kWtfChunk / 32; it += 4) {
+        float w[4][4];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) w[jj] = (jj < nj) ? __ldg(W + i + (size_t)(j0 + jj) * n) : 0.f;
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + (it + u) * 32 + lane;
 #pragma unroll
-            for (int c = 0; c < BP; ++c) f[c] = (c < b) ? F[i + (size_t)c * n] : 0.f;
+            for (int jj = 0; jj < 4; ++jj) w[u][jj] = i < n ? __ldg(wp[jj] + i) : 0.f;
+        }
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
+        for (int u = 0; u < 4; ++u) {
+            const int r = (it + u) * 32 + lane;
 #pragma unroll
-                for (int c = 0; c < BP; ++c) acc[jj][c] = fmaf(w[jj], f[c], acc[jj][c]);
+            for (int c = 0; c < BP; ++c) {
+                const float f = sF[c][r];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) acc[jj][c] = fmaf(w[u][jj], f, acc[jj][c]);
+            }
         }
     }
 #pragma unroll
@@ -446,17 +473,23 @@ wtf_partial_kernel(const float *__restrict__ W, const float *__restrict__ F, int
     }
 }
 
-// C[j + c ldc] = sum over chunks (fixed order); optionally Hk[j + c ldh] += the same value
+// C[j + c ldc] = sum over chunks in a fixed order (lane-strided partial sums, then a shuffle tree: the
+// same association on every run and every rank); optionally Hk[j + c ldh] (+)= the same value.
+// One warp per (j, c).
 template <int BP>
-__global__ void wtf_reduce_kernel(const float *__restrict__ partial, int chunks, int rows, int b,
-                                  float *__restrict__ C, int ldc, float *__restrict__ Hk, int ldh, int hk_assign)
+__global__ void __launch_bounds__(256)
+wtf_reduce_kernel(const float *__restrict__ partial, int chunks, int rows, int b,
+                  float *__restrict__ C, int ldc, float *__restrict__ Hk, int ldh, int hk_assign)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= rows * BP) return;
     const int j = t / BP, c = t % BP;
     float v = 0.f;
-    for (int ch = 0; ch < chunks; ++ch) v += partial[((size_t)ch * rows + j) * BP + c];
-    if (c < b) {
+    for (int ch = lane; ch < chunks; ch += 32) v += partial[((size_t)ch * rows + j) * BP + c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && c < b) {
         C[j + (size_t)c * ldc] = v;
         if (Hk) Hk[j + (size_t)c * ldh] = hk_assign ? v : Hk[j + (size_t)c * ldh] + v;
     }
@@ -484,12 +517,12 @@ fsub_kernel(const float *__restrict__ W, const float *__restrict__ C, int ldc, i
         if (i < n) {
             const float *wp = W + i + (size_t)jt * n;
             int j = 0;
-            for (; j + 8 <= nj; j += 8) {
-                float w[8];
+            for (; j + 16 <= nj; j += 16) {
+                float w[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) w[u] = __ldg(wp + (size_t)(j + u) * n);
+                for (int u = 0; u < 16; ++u) w[u] = __ldg(wp + (size_t)(j + u) * n);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < 16; ++u) {
 #pragma unroll
                     for (int q = 0; q < BP / 4; ++q) {
                         const float4 cv = *reinterpret_cast<const float4 *>(&cs[j + u][4 * q]);
@@ -635,8 +668,8 @@ struct KsState {
         const int chunks = (int)((n + kWtfChunk - 1) / kWtfChunk);
         dim3 g((rows + kWtfCols - 1) / kWtfCols, chunks);
         wtf_partial_kernel<BP><<<g, 256, 0, c.stream>>>(V.p, Fm, n, rows, cols, wpart.p);
-        wtf_reduce_kernel<BP><<<(rows * BP + 255) / 256, 256, 0, c.stream>>>(wpart.p, chunks, rows, cols, Cm, ldc, Hk,
-                                                                              ncv, assign ? 1 : 0);
+        wtf_reduce_kernel<BP><<<(rows * BP * 32 + 255) / 256, 256, 0, c.stream>>>(wpart.p, chunks, rows, cols, Cm, ldc, Hk,
+                                                                                   ncv, assign ? 1 : 0);
         count_launch(c, 2);
     }
     template <int BP>
