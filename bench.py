@@ -143,6 +143,18 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_traffic(config):
+    """DRAM bytes per SpMM pass from the committed ncu --set full capture (profiles/spmm_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "spmm_traffic.json")
+    try:
+        d = json.load(open(p))
+        if d.get("workload") == config:
+            return 0.5 * (float(d["pass1"]) + float(d["pass2"]))
+    except Exception:
+        pass
+    return None
+
+
 def run_ref_dump(c, k, nthreads, workdir):
     """Times the unmodified reference (oracle/_ref/ref_dump) on corpus `c`; returns stage seconds."""
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
@@ -153,7 +165,7 @@ def run_ref_dump(c, k, nthreads, workdir):
     env = dict(os.environ, OMP_THREAD_LIMIT=str(nthreads), OMP_NUM_THREADS=str(nthreads),
                OPENBLAS_NUM_THREADS=str(nthreads))
     t0 = time.perf_counter()
-    subprocess.run([exe, path, workdir, str(k)], check=True, env=env, stdout=subprocess.DEVNULL,
+    subprocess.run([exe, path, workdir, str(k), "--upto", "E"], check=True, env=env, stdout=subprocess.DEVNULL,
                    stderr=subprocess.DEVNULL)
     wall = time.perf_counter() - t0
     meta = json.load(open(os.path.join(workdir, "meta.json")))
@@ -320,6 +332,15 @@ def bench_ours(args):
                                    "dist_tc_ms", "dist_simt_ms", "dist_tc_flops", "dist_simt_flops", "lloyd_accum_ms",
                                    "spmm_head1_ms", "spmm_tail1_ms", "spmm_head2_ms", "spmm_tail2_ms", "spmm_head_words", "spmm_tail_nnz",
                                    "alloc_misses", "alloc_hits")}
+    # ---- SURVEY 8(f) row 1, reported beside the metric (not part of it): Lloyd on the full-dimensional B from
+    # the lifted centers the last step left on the device (trainer.cpp:566)
+    ctx.call("isle_cuda_reset_stats")
+    fobj, fit, fms = C.c_double(), C.c_int(), C.c_double()
+    ctx.call("isle_cuda_timer_start")
+    ctx.call("isle_cuda_lloyd_full", k, None, 10, None, C.byref(fobj), C.byref(fit))
+    ctx.call("isle_cuda_timer_stop", C.byref(fms))
+    stf = {n: ctx.stat(n) for n in ("lloyd_full_iter_ms", "lloyd_full_assign_ms", "lloyd_full_update_ms",
+                                    "lloyd_full_assign_flops")}
     ctx.call("isle_cuda_set_profiling", 0)
 
     # ---- (2) end to end: host buffers in, host results out, every step
@@ -365,12 +386,18 @@ def bench_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "B^T X and B Y passes of the operator: spmm_head_kernel (tcgen05 dense head) + "
                                                          "spmm_gather_bfp_kernel (tail)", "achieved": ach,
-                         "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None, "traffic": load_traffic(args.config),
                          "peak_source": peak_src, "launches": int(ncalls),
                          "avg_launch_ms": spmm_ms / ncalls if ncalls else None,
                          "bytes_per_launch": spmm_bytes / ncalls if ncalls else None},
             "stage_ms_per_step": {n[:-3]: st[n] / args.steps for n in st if n.endswith("_ms")},
             "step_wall_ms": [round(x, 2) for x in step_wall],
+            "next_rows": {"lloyd_full": {"what": "SURVEY 8(f) row 1: run_lloyds on the full-dimensional B (trainer.cpp:566), "
+                                                 "device-resident, not part of the metric", "ms": fms.value, "iters": fit.value,
+                                         "objective": fobj.value, "assign_ms": stf["lloyd_full_assign_ms"],
+                                         "update_ms": stf["lloyd_full_update_ms"],
+                                         "assign_gather_tflops": (stf["lloyd_full_assign_flops"] / (stf["lloyd_full_assign_ms"] * 1e-3) / 1e12
+                                                                  if stf["lloyd_full_assign_ms"] > 0 else None)}},
             "alloc": {"driver_allocs_in_timed_region": st["alloc_misses"], "cache_hits_per_step": st["alloc_hits"] / args.steps},
         }
         if not args.no_cpu_baseline and world == 1:

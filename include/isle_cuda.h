@@ -125,6 +125,20 @@ int isle_cuda_assign_projected(isle_cuda_ctx *ctx, uint64_t k, const float *cent
  * centers_out may be NULL (product computed, result left on the device: device-only timing). */
 int isle_cuda_lift_centers(isle_cuda_ctx *ctx, uint64_t ncols, const float *in, uint64_t ld_in,
                            float *centers_out);
+/* SURVEY 8(f) row 1.  Replaces FPSparseMatrix::run_lloyds (src/sparseMatrix.cpp:1679-1746, with
+ * lloyds_iter :1584-1667, distsq_docs_to_centers :1494-1552, closest_centers :1554-1569,
+ * compute_docs_l2sq :1670-1677): Lloyd's k-means on the full-dimensional B, the call that follows
+ * the spectral core in train() (src/trainer.cpp:566) and produces closest_docs.
+ * centers_inout: k centers of length V, center c contiguous (`centers + c * vocab_size`), updated
+ * in place; NULL = start from the centers the last isle_cuda_lift_centers left on the device and
+ * keep the result there (device-only timing).  Needs B only (may be called after
+ * isle_cuda_cleanup_eigensolver, as train() does).  Stops when the partition repeats or after
+ * max_reps iterations.  assign_out (D_B u32, may be NULL) = final partition (argmin |dist|, first
+ * index on ties; an empty cluster's center stays zero); *objective_out (may be NULL) =
+ * sum_d ||B_d - c_assign(d)||^2 in fp64 for the returned centers/partition; *iters_out (may be
+ * NULL) = iterations executed.  max_reps >= 1. */
+int isle_cuda_lloyd_full(isle_cuda_ctx *ctx, uint64_t k, float *centers_inout, int max_reps,
+                         uint32_t *assign_out, double *objective_out, int *iters_out);
 /* cleanup_after_eigensolver (src/sparseMatrix.cpp:1264-1275): frees U, P and solver state. */
 int isle_cuda_cleanup_eigensolver(isle_cuda_ctx *ctx);
 

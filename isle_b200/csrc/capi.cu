@@ -261,6 +261,15 @@ int isle_cuda_lloyd_projected(isle_cuda_ctx *h, uint64_t k, float *centers_inout
     });
 }
 
+int isle_cuda_lloyd_full(isle_cuda_ctx *h, uint64_t k, float *centers_inout, int max_reps, uint32_t *assign_out,
+                         double *objective_out, int *iters_out)
+{
+    return guarded(h, [&](Ctx &c) {
+        ISLE_REQUIRE(max_reps >= 1, ISLE_ERR_ARG, "lloyd_full: bad arguments");
+        lloyd_full(c, k, centers_inout, max_reps, assign_out, objective_out, iters_out);
+    });
+}
+
 int isle_cuda_assign_projected(isle_cuda_ctx *h, uint64_t k, const float *centers, uint32_t *assign_out)
 {
     return guarded(h, [&](Ctx &c) {

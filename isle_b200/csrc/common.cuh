@@ -245,6 +245,8 @@ struct Ctx {
     DevBuf<float> P;                       // DB x kp row-major, zero padded
     DevBuf<float> P_hi, P_lo;              // split-TF32 copies of P for the tcgen05 engine (dist_tc.cu)
     DevBuf<float> p_l2;                    // DB
+    DevBuf<float> lifted;                  // last lift_centers result (V x lifted_cols, column-major): input of lloyd_full
+    uint64_t lifted_cols = 0;
 
     // ---- stats / options
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
@@ -326,6 +328,10 @@ void lloyd_projected(Ctx &c, uint64_t k, float *centers_inout, int max_reps,
                      uint32_t *assign_out, double *objective_out, int *iters_out);
 void assign_projected(Ctx &c, uint64_t k, const float *centers, uint32_t *assign_out);
 void lift_centers(Ctx &c, uint64_t ncols, const float *in, uint64_t ld_in, float *out);
+
+// ---- lloyd_full.cu (run_lloyds on the full-dimensional B)
+void lloyd_full(Ctx &c, uint64_t k, float *centers_inout, int max_reps, uint32_t *assign_out,
+                double *objective_out, int *iters_out);
 
 // ---- dist_tc.cu (tcgen05 split-TF32 distance contraction)
 void split_tf32(Ctx &c, const float *x, size_t n, float *hi, float *lo);

@@ -704,13 +704,16 @@ void lift_centers(Ctx &c, uint64_t ncols, const float *in, uint64_t ld_in, float
     ISLE_REQUIRE(c.have_U, ISLE_ERR_ARG, "lift_centers: needs U");
     ISLE_REQUIRE(ld_in >= c.k, ISLE_ERR_ARG, "lift_centers: ld_in < k");   // :1445
     const int V = (int)c.V, k = (int)c.k, nc = (int)ncols;
-    DevBuf<float> din((size_t)ld_in * ncols), dout((size_t)V * ncols);
+    DevBuf<float> din((size_t)ld_in * ncols);
+    // the lifted centers stay on the device: they are the input of run_lloyds on the full-dimensional B (lloyd_full.cu)
+    c.lifted.alloc((size_t)V * ncols);
+    c.lifted_cols = ncols;
     ISLE_CUDA_CHECK(cudaMemcpyAsync(din.p, in, din.bytes(), cudaMemcpyHostToDevice, c.stream));
     const float one = 1.f, zero = 0.f;
     ISLE_CUBLAS_CHECK(cublasSgemm(c.cublas, CUBLAS_OP_N, CUBLAS_OP_N, V, nc, k, &one, c.U.p, V, din.p, (int)ld_in, &zero,
-                                  dout.p, V));
+                                  c.lifted.p, V));
     count_launch(c);
-    if (out) ISLE_CUDA_CHECK(cudaMemcpyAsync(out, dout.p, dout.bytes(), cudaMemcpyDeviceToHost, c.stream));
+    if (out) ISLE_CUDA_CHECK(cudaMemcpyAsync(out, c.lifted.p, c.lifted.bytes(), cudaMemcpyDeviceToHost, c.stream));
     ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }
 

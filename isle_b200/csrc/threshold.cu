@@ -211,6 +211,8 @@ void compute_thresholds(Ctx &c, uint64_t k, float *zetas_out, int64_t *new_nnz_o
     c.new_nnz = (int64_t)hk;
     c.have_zeta = true;
     c.have_B = c.have_csr = false;
+    c.lifted.release();
+    c.lifted_cols = 0;
     if (new_nnz_out) *new_nnz_out = (int64_t)hk;
 }
 

@@ -7,7 +7,7 @@
 // forwards to the C ABI in include/isle_cuda.h.  Explicit specialisations are ordinary (strong)
 // symbols, while the reference's `template class ISLE::FPSparseMatrix<float>;`
 // (src/sparseMatrix.cpp:2495-2510) emits weak ones, so the linker binds trainer.o to the
-// functions below and everything else (run_lloyds on full B, catchwords, topic model, output
+// functions below and everything else (catchwords, topic model, output
 // writers) keeps running the reference's host code on the arrays this file fills.
 //
 //   reference member (include/sparseMatrix.h)            line   C ABI entry point
@@ -22,6 +22,7 @@
 //   FPSparseMatrix::run_lloyds_on_projected_space         :434   isle_cuda_lloyd_projected
 //   FPSparseMatrix::left_multiply_by_U_Spectra            :309   isle_cuda_lift_centers
 //   FPSparseMatrix::cleanup_after_eigensolver             :260   isle_cuda_cleanup_eigensolver
+//   FPSparseMatrix::run_lloyds          :370   isle_cuda_lloyd_full
 //
 // Ownership follows the reference: every host array is new[]-allocated here to the size the
 // reference would have used and filled by the library; device memory belongs to the context.
@@ -265,5 +266,31 @@ namespace ISLE
         assert(U_rows == (MKL_INT)vocab_size());
         assert(ld_in >= (doc_id_t)U_cols);
         check(isle_cuda_lift_centers(ctx(), ncols, in, ld_in, out), "lift_centers");
+    }
+
+    // ---- stage F ------------------------------------------------------------
+    // run_lloyds (src/sparseMatrix.cpp:1679-1746), called from src/trainer.cpp:566 with the lifted
+    // centers and closest_docs: the host `centers` array is the input and receives the result.
+    template<>
+    float FPSparseMatrix<float>::run_lloyds(
+        const doc_id_t num_centers,
+        float *centers,
+        std::vector<doc_id_t> *closest_docs,
+        const int max_reps)
+    {
+        std::vector<uint32_t> assign;
+        if (closest_docs != NULL) {
+            for (doc_id_t center = 0; center < num_centers; ++center)
+                assert(closest_docs[center].size() == 0);
+            assign.resize(num_docs());
+        }
+        int iters = 0;
+        check(isle_cuda_lloyd_full(ctx(), num_centers, centers, max_reps,
+                                   closest_docs ? assign.data() : NULL, NULL, &iters), "lloyd_full");
+        std::cout << "Lloyd's on B: " << iters << " iterations on the device\n";
+        if (closest_docs != NULL)
+            for (doc_id_t d = 0; d < num_docs(); ++d)
+                closest_docs[assign[d]].push_back(d);            // ascending doc ids, as :1652-1653
+        return 0.0f;                                             // compute_residual is off in the reference (:1588)
     }
 }

@@ -35,6 +35,7 @@ BLOCK_KS_MAX_ITERS = 100
 BLOCK_KS_TOLERANCE = 1e-4
 KMEANS_INIT_REPS = 1
 MAX_KMEANS_LOWD_REPS = 10
+MAX_KMEANS_REPS = 10           # include/hyperparams.h:68
 
 
 class SparseMatrix:
@@ -241,6 +242,29 @@ class FPSparseMatrix:
         pc = np.ascontiguousarray(projected_centers, dtype=np.float32)
         self.ctx.call("isle_cuda_assign_projected", int(num_centers), ptr(pc), ptr(assign))
         return assign
+
+    def run_lloyds(self, num_centers: int, centers: np.ndarray, closest_docs: Optional[List[list]] = None,
+                   max_reps: int = MAX_KMEANS_REPS) -> float:
+        """src/sparseMatrix.cpp:1679-1746: Lloyd's on the full-dimensional B.
+        ``centers`` is (k, V) float32 C-contiguous, center c = row c (the reference's
+        ``centers + c * vocab_size``), updated in place; pass None to start from the centers the last
+        left_multiply_by_U_Spectra left on the device.  ``closest_docs`` (list of k lists) receives the
+        partition.  Returns the residual the reference returns (0: compute_residual is off, :1588);
+        assignment, objective and iteration count are kept in ``self.last_lloyd_full``."""
+        k = int(num_centers)
+        if centers is not None:
+            assert centers.dtype == np.float32 and centers.flags["C_CONTIGUOUS"]
+            assert centers.shape == (k, self._vocab_size)
+        assign = np.zeros(self._num_docs, dtype=np.uint32)
+        obj, iters = C.c_double(), C.c_int()
+        self.ctx.call("isle_cuda_lloyd_full", k, ptr(centers), int(max_reps), ptr(assign), C.byref(obj), C.byref(iters))
+        self.last_lloyd_full = dict(assign=assign, objective=float(obj.value), iters=int(iters.value))
+        if closest_docs is not None:
+            order = np.argsort(assign, kind="stable")
+            bounds = np.searchsorted(assign[order], np.arange(k + 1))
+            for c in range(k):
+                closest_docs[c][:] = order[bounds[c]:bounds[c + 1]].tolist()
+        return 0.0
 
     def left_multiply_by_U_Spectra(self, inp: np.ndarray, ld_in: int, ncols: int) -> np.ndarray:
         """src/sparseMatrix.cpp:1438-1450: out (V x ncols) = U * in, ``inp`` holds ncols columns of

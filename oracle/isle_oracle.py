@@ -429,6 +429,66 @@ def lift_centers(U, C_lowd):
     return (U.astype(F32) @ C_lowd.T.astype(F32)).astype(F32)
 
 
+# --------------------------------------------------------------------------- stage F
+def docs_l2sq_full(B_csc):
+    """src/sparseMatrix.cpp:1670-1677 compute_docs_l2sq: sum of squared entries per column of B."""
+    Bc = B_csc.tocsc()
+    sq = (Bc.data.astype(F32) * Bc.data.astype(F32)).astype(F32)
+    return np.add.reduceat(np.concatenate([sq, [F32(0)]]), Bc.indptr[:-1]).astype(F32) * (np.diff(Bc.indptr) > 0)
+
+
+def dist_matrix_full(B_csc, d2, C):
+    """src/sparseMatrix.cpp:1494-1552 distsq_docs_to_centers: ((-2 B^T C^T) + ||c||^2) + ||d||^2.
+    C is (k, V): center c = row c (the reference's `centers + c * vocab_size`)."""
+    C = C.astype(F32)
+    c2 = np.einsum("ij,ij->i", C, C, dtype=F32).astype(F32)
+    G = (F32(-2.0) * np.asarray(B_csc.T.astype(F32) @ C.T, dtype=F32)).astype(F32)
+    return ((G + c2[None, :]).astype(F32) + d2[:, None]).astype(F32)
+
+
+def lloyds_iter_full(B_csc, d2, C):
+    """src/sparseMatrix.cpp:1584-1667 lloyds_iter: assign by cblas_isamin (first index of min |x|),
+    then center = sum of member columns / cluster size; an empty cluster's center stays zero."""
+    import scipy.sparse as sp
+    k = C.shape[0]
+    a = np.argmin(np.abs(dist_matrix_full(B_csc, d2, C)), axis=1).astype(np.uint32)
+    D = B_csc.shape[1]
+    M = sp.csr_matrix((np.ones(D, dtype=np.float64), (np.arange(D), a.astype(np.int64))), shape=(D, k))
+    newC = np.asarray((B_csc.astype(np.float64) @ M).todense()).T.copy()
+    cnt = np.bincount(a, minlength=k)
+    nz = cnt > 0
+    newC[nz] /= cnt[nz][:, None]
+    return newC.astype(F32), a
+
+
+def run_lloyds_full(B_csc, C0, max_reps=10):
+    """src/sparseMatrix.cpp:1679-1746 run_lloyds on the full-dimensional B; stops when the partition
+    repeats.  (The reference's check lags by up to two iterations on an already fixed partition --
+    prev_closest_docs is only refreshed when the cluster sizes did not change, :1718-1733 -- which
+    cannot change the centers or the partition it returns.)"""
+    d2 = docs_l2sq_full(B_csc)
+    C = C0.astype(F32).copy()
+    prev, a, iters = None, None, 0
+    for _ in range(max_reps):
+        C, a = lloyds_iter_full(B_csc, d2, C)
+        iters += 1
+        if prev is not None and np.array_equal(prev, a):
+            break
+        prev = a
+    return C, a, iters
+
+
+def kmeans_objective_full(B_csc, C, a):
+    """Harness-side objective sum_d ||B_d - c_a(d)||^2 in fp64."""
+    Bc = B_csc.tocsc().astype(np.float64)
+    C = C.astype(np.float64)
+    c2 = np.einsum("ij,ij->i", C, C)
+    d2 = np.asarray(Bc.multiply(Bc).sum(0)).ravel()
+    docs = np.repeat(np.arange(Bc.shape[1]), np.diff(Bc.indptr))
+    dots = np.bincount(docs, weights=Bc.data * C[a.astype(np.int64)[docs], Bc.indices], minlength=Bc.shape[1])
+    return float((d2 - 2.0 * dots + c2[a.astype(np.int64)]).sum())
+
+
 # --------------------------------------------------------------------------- comparisons
 def principal_angle_sin(U1, U2):
     """sin of the largest principal angle between span(U1) and span(U2) (orthonormal cols)."""

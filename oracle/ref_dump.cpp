@@ -14,13 +14,14 @@
  *   stage C  initialize_for_eigensolver + compute_block_ks     (:492-497)
  *   stage D  kmeans_init_on_projected_space     (:529-530)
  *   stage E  run_lloyds_on_projected_space + left_multiply_by_U_Spectra (:546-550)
+ *   stage F  run_lloyds on the full-dimensional B   (:559-571)
  *
  * Input : <corpus.bin>  = int64 V, D, nnz ; int64 offsets[D+1] ; uint32 rows[nnz] ;
  *                         uint32 counts[nnz]      (doc-major CSC of raw counts)
  * Output: <outdir>/<name>.bin raw little-endian arrays + meta.json with sizes and
  *         per-stage wall-clock seconds (used as the CPU baseline by bench.py).
  *
- * usage: ref_dump <corpus.bin> <outdir> <k> [--upto A|B|C|D|E] [--mask mask.u8]
+ * usage: ref_dump <corpus.bin> <outdir> <k> [--upto A|B|C|D|E|F] [--mask mask.u8]
  *                 [--centers centers_lowd.f32]   (override k-means++ seeds for Lloyd)
  *                 [--lloyd-iters n] [--srand seed]
  */
@@ -91,7 +92,7 @@ int main(int argc, char **argv)
     }
     const std::string corpus = argv[1], out = argv[2];
     const doc_id_t k = (doc_id_t)std::atol(argv[3]);
-    char upto = 'E';
+    char upto = 'F';
     std::string mask_file, centers_file;
     int lloyd_iters = MAX_KMEANS_LOWD_REPS;
     for (int i = 4; i < argc; ++i) {
@@ -241,9 +242,25 @@ int main(int argc, char **argv)
         dump(out, "centers", centers.data(), centers.size());
     }
     delete[] closest;
-    std::fprintf(meta, ", \"t_lloyd\": %.6f}\n", t_ll);
+    std::fprintf(meta, ", \"t_lloyd\": %.6f", t_ll);
+    B->cleanup_after_eigensolver();                       /* trainer.cpp:554 */
+    if (upto == 'E') { std::fprintf(meta, "}\n"); std::fclose(meta); return 0; }
+
+    /* ---- stage F: Lloyd on the full-dimensional B (trainer.cpp:559-571) ---- */
+    t0 = now_s();
+    auto closest_full = new std::vector<doc_id_t>[k];
+    B->run_lloyds(k, centers.data(), closest_full, MAX_KMEANS_REPS);
+    double t_lf = now_s() - t0;
+    {
+        std::vector<uint32_t> assign((size_t)DB, 0xffffffffu);
+        for (doc_id_t c = 0; c < k; ++c)
+            for (auto d : closest_full[c]) assign[d] = (uint32_t)c;
+        dump(out, "full_assign", assign.data(), assign.size());
+        dump(out, "full_centers", centers.data(), centers.size());
+    }
+    delete[] closest_full;
+    std::fprintf(meta, ", \"t_lloyd_full\": %.6f}\n", t_lf);
     std::fclose(meta);
-    B->cleanup_after_eigensolver();
     delete B;
     delete A_sp;
     return 0;

@@ -30,6 +30,16 @@ def golden_c1():
 
 
 @pytest.fixture(scope="session")
+def golden_tiny_stageF():
+    return dict(np.load(os.path.join(GOLDEN, "tiny_stageF.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_c1_stageF():
+    return dict(np.load(os.path.join(GOLDEN, "c1_stageF.npz")))
+
+
+@pytest.fixture(scope="session")
 def corpus_c1():
     from isle_b200 import corpus
     return corpus.generate("c1")

@@ -59,7 +59,24 @@ def run(name, extra=()):
     return c, tmp, out, ld
 
 
+def stage_f(name):
+    """Stage F (run_lloyds on the full-dimensional B) as a self-contained fixture:
+    zetas (-> B), the lifted centers that went in, the centers and the partition that came out."""
+    c, tmp, out, ld = run(name)
+    return dict(zetas=out["zetas"], corpus_sha=out["corpus_sha"], B_sha=out["B_sha"],
+                centers_in=ld("centers", np.float32), centers_out=ld("full_centers", np.float32),
+                assign=ld("full_assign", np.uint32))
+
+
+def main_stage_f():
+    here = os.path.dirname(__file__)
+    for name in ("tiny", "c1"):
+        np.savez_compressed(os.path.join(here, f"{name}_stageF.npz"), **stage_f(name))
+
 if __name__ == "__main__":
+    if "--stage-f" in sys.argv:      # adds the stage-F fixtures without touching the stage A-E ones
+        main_stage_f()
+        sys.exit(0)
     here = os.path.dirname(__file__)
     c, tmp, out, ld = run("tiny")
     out.update(offsets=c.offsets, rows=c.rows, counts=c.counts,
@@ -83,4 +100,5 @@ if __name__ == "__main__":
 
     c, tmp, out, ld = run("c1")
     np.savez_compressed(os.path.join(here, "c1.npz"), **out)
-    print("golden fixtures written:", os.listdir(here))
+
+    main_stage_f()

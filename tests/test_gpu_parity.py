@@ -320,6 +320,78 @@ def test_kmeanspp_invariants(ctx, golden_tiny):
     assert pot(seeds.astype(np.int64)) < uni
 
 
+# ---------------------------------------------------------------- stage F: Lloyd on the full-dimensional B
+def _stage_f_B(ctx, g, c):
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    A, B, zetas, nn, oc = make_AB(ctx, c.V, c.D, c.k, vals, c.rows, c.offsets, avg, nz)
+    assert np.array_equal(zetas, g["zetas"])
+    bv, br, bo, _ = O.threshold_and_copy(vals, c.rows, c.offsets, g["zetas"])
+    return B, O.to_csc(bv, br, bo, c.V)
+
+
+@pytest.mark.parametrize("name", ["tiny", "c1"])
+def test_lloyd_full_matches_reference(ctx, name, golden_tiny_stageF, golden_c1_stageF, corpus_c1):
+    """SURVEY 8(f) row 1 (run_lloyds, src/sparseMatrix.cpp:1679-1746) through the C ABI against the
+    reference's own output for the same B and the same starting centers."""
+    from isle_b200 import corpus
+    g = golden_tiny_stageF if name == "tiny" else golden_c1_stageF
+    c = corpus.generate("tiny") if name == "tiny" else corpus_c1
+    B, Bo = _stage_f_B(ctx, g, c)
+    C = np.ascontiguousarray(g["centers_in"].reshape(c.k, c.V).copy())
+    closest = [[] for _ in range(c.k)]
+    assert B.run_lloyds(c.k, C, closest, 10) == 0.0
+    a = B.last_lloyd_full["assign"]
+    C_ref = g["centers_out"].reshape(c.k, c.V)
+    assert np.mean(a != g["assign"]) <= 1e-3                      # identical partition, near-ties excepted
+    assert np.max(np.abs(C - C_ref)) <= 1e-5 * np.max(np.abs(C_ref))
+    o_ref = O.kmeans_objective_full(Bo, C_ref, g["assign"])
+    assert abs(B.last_lloyd_full["objective"] - o_ref) <= 1e-5 * o_ref
+    assert abs(O.kmeans_objective_full(Bo, C, a) - B.last_lloyd_full["objective"]) <= 1e-5 * o_ref
+    # closest_docs: a partition of all documents, ascending ids per cluster (trainer.cpp:567-570)
+    assert sum(len(x) for x in closest) == B.num_docs()
+    assert all(x == sorted(x) for x in closest)
+    assert all(a[d] == t for t in range(c.k) for d in closest[t][:3])
+    # oracle restatement from the same start agrees as well, iteration count included
+    C_o, a_o, it_o = O.run_lloyds_full(Bo, g["centers_in"].reshape(c.k, c.V), 10)
+    assert np.mean(a != a_o) <= 1e-3 and B.last_lloyd_full["iters"] == it_o
+
+
+def test_lloyd_full_single_iteration_and_empty_cluster(ctx, golden_tiny_stageF):
+    """One lloyds_iter (src/sparseMatrix.cpp:1584-1667) against the oracle; a center nobody is
+    closest to is left at zero (:1626, :1655-1661); max_reps is honoured."""
+    from isle_b200 import corpus
+    g, c = golden_tiny_stageF, corpus.generate("tiny")
+    B, Bo = _stage_f_B(ctx, g, c)
+    C0 = g["centers_in"].reshape(c.k, c.V).copy()
+    C0[3] = 1e3                                                   # far from every document
+    C = np.ascontiguousarray(C0.copy())
+    B.run_lloyds(c.k, C, None, 1)
+    assert B.last_lloyd_full["iters"] == 1
+    C_o, a_o = O.lloyds_iter_full(Bo, O.docs_l2sq_full(Bo), C0)
+    assert np.array_equal(B.last_lloyd_full["assign"], a_o)
+    assert not np.any(a_o == 3) and np.all(C[3] == 0.0)
+    assert np.max(np.abs(C - C_o)) <= 1e-5 * np.max(np.abs(C_o))
+
+
+def test_lloyd_full_from_device_resident_lifted_centers(ctx, golden_tiny):
+    """train() order (src/trainer.cpp:550-566): lift the projected centers, clean up the eigensolver,
+    then run_lloyds on B.  With centers=None the library starts from the lifted centers it kept on the
+    device; the result must equal the host round trip."""
+    g = golden_tiny
+    A, B, zetas, nn, oc = tiny_AB(ctx, g)
+    k, V = int(g["k"]), int(g["V"])
+    B.set_U(g["U_colmajor"].reshape(k, V).T)
+    Cl = np.ascontiguousarray(g["centers_lowd_final"].reshape(k, k))
+    lifted = B.left_multiply_by_U_Spectra(Cl, k, k)              # V x k, also kept on the device
+    B.cleanup_after_eigensolver()
+    B.run_lloyds(k, None, None, 10)
+    dev = dict(B.last_lloyd_full)
+    C = np.ascontiguousarray(lifted.T.copy())
+    B.run_lloyds(k, C, None, 10)
+    assert np.array_equal(dev["assign"], B.last_lloyd_full["assign"])
+    assert dev["iters"] == B.last_lloyd_full["iters"] and dev["objective"] == B.last_lloyd_full["objective"]
+
+
 # ---------------------------------------------------------------- end to end
 def test_spectral_core_end_to_end_c1(ctx, golden_c1, corpus_c1):
     """Stages A-E through the public call; k-means is checked through rotation-invariant

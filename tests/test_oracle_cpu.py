@@ -185,6 +185,29 @@ def test_lloyd_c1_matches_reference(golden_c1, corpus_c1):
     assert O.principal_angle_sin(U, U_ref) < 1e-3
 
 
+def _stage_f_oracle(g, c):
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    bv, br, bo, _ = O.threshold_and_copy(vals, c.rows, c.offsets, g["zetas"])
+    B = O.to_csc(bv, br, bo, c.V)
+    return B, O.run_lloyds_full(B, g["centers_in"].reshape(c.k, c.V), 10)
+
+
+@pytest.mark.parametrize("name", ["tiny", "c1"])
+def test_lloyd_full_matches_reference(name, golden_tiny_stageF, golden_c1_stageF, corpus_c1):
+    """the restatement of run_lloyds on the full-dimensional B against the
+    reference's own output (tests/golden/*_stageF.npz, made by ref_dump stage F)."""
+    from isle_b200 import corpus
+    g = golden_tiny_stageF if name == "tiny" else golden_c1_stageF
+    c = corpus.generate("tiny") if name == "tiny" else corpus_c1
+    B, (C, a, iters) = _stage_f_oracle(g, c)
+    C_ref = g["centers_out"].reshape(c.k, c.V)
+    assert np.mean(a != g["assign"]) <= 1e-3
+    assert np.max(np.abs(C - C_ref)) <= 1e-5 * np.max(np.abs(C_ref))
+    o, o_ref = O.kmeans_objective_full(B, C, a), O.kmeans_objective_full(B, C_ref, g["assign"])
+    assert abs(o - o_ref) <= 1e-6 * o_ref
+    assert 1 <= iters <= 10
+
+
 def test_kmeanspp_invariants(golden_tiny):
     g = golden_tiny
     V, k = int(g["V"]), int(g["k"])
