@@ -41,6 +41,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ISLETrain spectral-core docs/sec (threshold -> block-KS SVD -> k-means on projection)"
 UNIT = "docs/s"
+SHAPES = {"c1": "small synthetic", "c2": "NYTimes-shaped synthetic", "c3": "PubMed-shaped synthetic",
+          "c3s": "PubMed-shaped synthetic, one of 8 document shards", "c4": "Wikipedia-shaped synthetic"}
 
 
 def parse():
@@ -330,7 +332,8 @@ def bench_ours(args):
                                    "ks_truncate_ms", "ks_restarts", "project_ms", "lloyd_iter_ms", "pp_round_ms",
                                    "thr_hist_ms", "thr_zeta_ms", "b_count_ms", "b_compact_ms", "csr_build_ms",
                                    "dist_tc_ms", "dist_simt_ms", "dist_tc_flops", "dist_simt_flops", "lloyd_accum_ms",
-                                   "spmm_head1_ms", "spmm_tail1_ms", "spmm_head2_ms", "spmm_tail2_ms", "spmm_head_words", "spmm_tail_nnz",
+                                   "ks_wtf_ms", "ks_wtf_bytes", "ks_wtfred_ms", "ks_fsub_ms", "ks_fsub_bytes", "pp_dist_tc_ms",
+                                   "pp_dist_skinny_ms", "pp_dist_simt_ms", "split_p_ms", "spmm_head1_ms", "spmm_tail1_ms", "spmm_head2_ms", "spmm_tail2_ms", "spmm_head_words", "spmm_tail_nnz",
                                    "alloc_misses", "alloc_hits")}
     # ---- SURVEY 8(f) row 1, reported beside the metric (not part of it): Lloyd on the full-dimensional B from
     # the lifted centers the last step left on the device (trainer.cpp:566)
@@ -375,7 +378,7 @@ def bench_ours(args):
             "metric": METRIC, "value": total_docs * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config} NYTimes-shaped synthetic per GPU: {D} docs x {V} vocab, {nnz} nnz, k={k}",
+            "config": {"workload": f"{args.config} {SHAPES.get(args.config, 'synthetic')} per GPU: {D} docs x {V} vocab, {nnz} nnz, k={k}",
                        "block_size": 10, "tol": 1e-4, "l2": "inputs (A: %.0f MB) larger than the 126 MB L2" % (nnz * 8 / 1e6),
                        "D_B": state["DB"], "nnz_B": state["nnzB"], "ks_restarts": st["ks_restarts"],
                        "spmm_head_words": int(st["spmm_head_words"]), "spmm_tail_nnz": int(st["spmm_tail_nnz"]),
@@ -391,6 +394,8 @@ def bench_ours(args):
                          "avg_launch_ms": spmm_ms / ncalls if ncalls else None,
                          "bytes_per_launch": spmm_bytes / ncalls if ncalls else None},
             "stage_ms_per_step": {n[:-3]: st[n] / args.steps for n in st if n.endswith("_ms")},
+            "panel_gbs": {"wtf": st["ks_wtf_bytes"] / st["ks_wtf_ms"] / 1e6 if st["ks_wtf_ms"] else None,
+                          "fsub": st["ks_fsub_bytes"] / st["ks_fsub_ms"] / 1e6 if st["ks_fsub_ms"] else None},
             "step_wall_ms": [round(x, 2) for x in step_wall],
             "next_rows": {"lloyd_full": {"what": "SURVEY 8(f) row 1: run_lloyds on the full-dimensional B (trainer.cpp:566), "
                                                  "device-resident, not part of the metric", "ms": fms.value, "iters": fit.value,

@@ -139,6 +139,13 @@ int isle_cuda_lift_centers(isle_cuda_ctx *ctx, uint64_t ncols, const float *in, 
  * NULL) = iterations executed.  max_reps >= 1. */
 int isle_cuda_lloyd_full(isle_cuda_ctx *ctx, uint64_t k, float *centers_inout, int max_reps,
                          uint32_t *assign_out, double *objective_out, int *iters_out);
+/* Harness only (no reference counterpart): one block Gram-Schmidt pass of BlockKs::expand
+ * (block-ks/restarted_block_ks.h:83-84) on caller data, C = W^T F then F -= W C, with a chosen engine
+ * (0 = fp32 FMA, 1 = fp32 FMA with vector loads, 2 = tcgen05 split TF32), so the panel engines of the
+ * device eigensolver can be checked in isolation.  W: n x rows column-major (ld n); F: n x b
+ * column-major (ld n), updated in place; C_out: rows x b column-major (ld rows). */
+int isle_cuda_panel_products(isle_cuda_ctx *ctx, int64_t n, int rows, int b, const float *W,
+                             float *F_inout, float *C_out, int engine);
 /* cleanup_after_eigensolver (src/sparseMatrix.cpp:1264-1275): frees U, P and solver state. */
 int isle_cuda_cleanup_eigensolver(isle_cuda_ctx *ctx);
 

@@ -70,6 +70,8 @@ CONFIGS = {
     "c2": dict(V=102000, D=300000, k=100, mu=5.93, seed=20242),
     "c3": dict(V=141000, D=8200000, k=2000, mu=4.29, seed=20243),
     "c4": dict(V=100000, D=11000000, k=2000, mu=4.485, seed=20244),
+    # one of the eight document shards of c3 (what each GPU of an 8 x B200 box holds): same V, k, mu
+    "c3s": dict(V=141000, D=1025000, k=2000, mu=4.29, seed=20243),
 }
 
 

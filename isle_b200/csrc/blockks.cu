@@ -547,21 +547,164 @@ fsub_kernel(const float *__restrict__ W, const float *__restrict__ C, int ldc, i
     }
 }
 
+// ---- vector-load variant of wtf for 16-byte aligned columns (n % 4 == 0): 128 KB in flight per SM.
+// Same arithmetic and fixed-order reductions, different tiling.  Measured (profiles/r1h): 2.25 vs 2.15 TB/s at
+// k = 2000 -- both variants are bound by the FMA / shared-memory rate of a 6 flop/byte SIMT product, not by
+// the bytes in flight (an 8-group vector variant of fsub was slower than the scalar kernel and was dropped).
+static constexpr int kWtf2Chunk = 1024;   // rows of W per CTA = 8 slabs of 128 rows (32 lanes x float4)
+static constexpr int kWtf2Cols = 32;      // columns of W per CTA: 16 warps x 2
+
+template <int BP>
+__global__ void __launch_bounds__(512, 1)
+wtf_partial_v2_kernel(const float *__restrict__ W, const float *__restrict__ F, int64_t n, int rows, int b,
+                      float *__restrict__ partial /* [chunks][rows][BP] */)
+{
+    extern __shared__ float4 sF4[];       // [BP][256] float4 = this CTA's 1024-row slice of F, column by column
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i0 = (int64_t)blockIdx.y * kWtf2Chunk;
+    const int j0 = blockIdx.x * kWtf2Cols + warp * 2;
+    const int nj = min(2, rows - j0);     // <= 0: this warp only helps staging F
+    // 1. all 16 W loads of this warp go out first (8 KB in flight per warp)
+    float4 w[2][8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int64_t i = i0 + u * 128 + lane * 4;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+            w[jj][u] = (i < n && jj < nj) ? __ldg(reinterpret_cast<const float4 *>(W + (size_t)(j0 + jj) * n + i))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // 2. F slice -> shared memory
+    for (int t = threadIdx.x; t < BP * 256; t += 512) {
+        const int c = t >> 8, r4 = t & 255;
+        const int64_t i = i0 + r4 * 4;
+        sF4[t] = (c < b && i < n) ? __ldg(reinterpret_cast<const float4 *>(F + (size_t)c * n + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    if (nj <= 0) return;
+    float acc[2][BP];
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int c = 0; c < BP; ++c) acc[jj][c] = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int c = 0; c < BP; ++c) {
+            const float4 f = sF4[c * 256 + u * 32 + lane];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+                acc[jj][c] = fmaf(w[jj][u].x, f.x, fmaf(w[jj][u].y, f.y, fmaf(w[jj][u].z, f.z, fmaf(w[jj][u].w, f.w, acc[jj][c]))));
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+#pragma unroll
+        for (int c = 0; c < BP; ++c) {
+            float v = acc[jj][c];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[jj][c] = v;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+            if (jj < nj) {
+#pragma unroll
+                for (int c = 0; c < BP; ++c)
+                    partial[((size_t)blockIdx.y * rows + (j0 + jj)) * BP + c] = acc[jj][c];
+            }
+    }
+}
+
+// The fp32 FMA panel engine: W^T F and F -= W C for a basis W of n rows (ld n) and at most ncv columns.
+struct PanelSimt {
+    Ctx &c;
+    int64_t n = 0;
+    int ncv = 0;
+    bool vec = true;                   // vector-load W^T F when the columns are 16-byte aligned
+    DevBuf<float> wpart;
+    explicit PanelSimt(Ctx &ctx) : c(ctx) {}
+    void init(int64_t n_, int ncv_, bool vec_)
+    {
+        n = n_; ncv = ncv_; vec = vec_;
+        const int chunks = (int)((n + kWtfChunk - 1) / kWtfChunk);
+        wpart.alloc((size_t)chunks * ncv * kMaxB);
+    }
+
+    // Cm(rows x b, ld ldc) = W^T Fm with W = V[:, 0:rows); when Hk != nullptr, Hk (ld ncv) is assigned
+    // (first pass) or incremented (correction passes) by the same coefficients.
+    template <int BP>
+    void wtf_t(const float *W, int rows, int cols, const float *Fm, float *Cm, int ldc, float *Hk, bool assign)
+    {
+        const bool v2 = vec && n % 4 == 0;
+        const int chunk_rows = v2 ? kWtf2Chunk : kWtfChunk;
+        const int chunks = (int)((n + chunk_rows - 1) / chunk_rows);
+        {
+            StatScope s(c, "ks_wtf", (double)n * rows * 4.0, 2.0 * (double)n * rows * cols);
+            if (v2) {
+                const int smem = BP * 256 * (int)sizeof(float4);
+                static bool attr_set = false;       // one instantiation per BP: set once per process
+                if (!attr_set) {
+                    ISLE_CUDA_CHECK(cudaFuncSetAttribute(wtf_partial_v2_kernel<BP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                    attr_set = true;
+                }
+                dim3 g((rows + kWtf2Cols - 1) / kWtf2Cols, chunks);
+                wtf_partial_v2_kernel<BP><<<g, 512, smem, c.stream>>>(W, Fm, n, rows, cols, wpart.p);
+            } else {
+                dim3 g((rows + kWtfCols - 1) / kWtfCols, chunks);
+                wtf_partial_kernel<BP><<<g, 256, 0, c.stream>>>(W, Fm, n, rows, cols, wpart.p);
+            }
+        }
+        {
+            StatScope s(c, "ks_wtfred", (double)chunks * rows * BP * 4.0);
+            wtf_reduce_kernel<BP><<<(rows * BP * 32 + 255) / 256, 256, 0, c.stream>>>(wpart.p, chunks, rows, cols, Cm, ldc, Hk,
+                                                                                       ncv, assign ? 1 : 0);
+        }
+        count_launch(c, 2);
+    }
+    template <int BP>
+    void fsub_t(const float *W, int rows, int cols, const float *Cm, int ldc, float *Fm)
+    {
+        StatScope s(c, "ks_fsub", (double)n * rows * 4.0, 2.0 * (double)n * rows * cols);
+        fsub_kernel<BP><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(W, Cm, ldc, n, rows, cols, Fm);
+        count_launch(c);
+    }
+    void wtf(const float *W, int rows, int cols, const float *Fm, float *Cm, int ldc, float *Hk, bool assign)
+    {
+        if (cols <= 4) wtf_t<4>(W, rows, cols, Fm, Cm, ldc, Hk, assign);
+        else if (cols <= 8) wtf_t<8>(W, rows, cols, Fm, Cm, ldc, Hk, assign);
+        else if (cols <= 12) wtf_t<12>(W, rows, cols, Fm, Cm, ldc, Hk, assign);
+        else wtf_t<16>(W, rows, cols, Fm, Cm, ldc, Hk, assign);
+    }
+    void fsub(const float *W, int rows, int cols, const float *Cm, int ldc, float *Fm)
+    {
+        if (cols <= 4) fsub_t<4>(W, rows, cols, Cm, ldc, Fm);
+        else if (cols <= 8) fsub_t<8>(W, rows, cols, Cm, ldc, Fm);
+        else if (cols <= 12) fsub_t<12>(W, rows, cols, Cm, ldc, Fm);
+        else fsub_t<16>(W, rows, cols, Cm, ldc, Fm);
+    }
+};
+
 struct KsState {
     Ctx &c;
     int64_t n;
     int k, b, ncv, m;
-    DevBuf<float> V, H, F, C, Rb, Tm, Wev, S, theta, Vtmp, Htmp, pack, work, wpart;
+    DevBuf<float> V, H, F, C, Rb, Tm, Wev, S, theta, Vtmp, Htmp, pack, work;
+    PanelSimt ps;
     DevBuf<double> qa, qq, qpart, cpart;
     int chol_grid = 1, gs_passes = 3;
-    bool fast_qr = true, custom_orth = true;
+    bool fast_qr = true, custom_orth = true, panel_v2 = true, panel_tc = true;
+    int panel_tc_min_rows = 0;
+    PanelTc ptc;
     DevBuf<int> drank, dinfo;
     int lwork = 0;
     int qr_grid = 1;
     int H_rows = 0, H_cols = 0;
     uint64_t seed, rng_calls = 0;
 
-    KsState(Ctx &ctx, int k_, int b_, uint64_t seed_) : c(ctx), n((int64_t)ctx.V), k(k_), b(b_), seed(seed_)
+    KsState(Ctx &ctx, int k_, int b_, uint64_t seed_) : c(ctx), n((int64_t)ctx.V), k(k_), b(b_), ps(ctx), seed(seed_)
     {
         ncv = 2 * k + b;
         m = ncv - b;
@@ -598,10 +741,14 @@ struct KsState {
         ISLE_REQUIRE(per_sm >= 1, ISLE_ERR_CUDA, "cholqr2_kernel cannot be made resident");
         chol_grid = std::max(1, std::min((int)((n + 15) / 16), c.num_sms));   // every CTA re-sums all partials: keep them few
         cpart.alloc((size_t)2 * chol_grid * 256);
-        const int chunks = (int)((n + kWtfChunk - 1) / kWtfChunk);
-        wpart.alloc((size_t)chunks * ncv * kMaxB);
         fast_qr = c.opt("ks_fast_qr", 1) != 0;
         custom_orth = c.opt("ks_custom_orth", 1) != 0;
+        panel_v2 = c.opt("ks_panel_v2", 1) != 0;
+        ps.init(n, ncv, panel_v2);
+        // tensor-core panel products (panel_tc.cu) once the basis has at least this many columns
+        panel_tc = c.opt("ks_panel_tc", 1) != 0 && PanelTc::usable(n) && b <= 16;
+        panel_tc_min_rows = c.opt("ks_panel_tc_min_rows", 0);
+        if (panel_tc) ptc.init(c, n, ncv);
         gs_passes = std::max(2, std::min(3, c.opt("ks_gs_passes", 3)));
     }
 
@@ -658,39 +805,6 @@ struct KsState {
         ISLE_CUBLAS_CHECK(cublasSgemm(c.cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, cols, rows, &mone, A, (int)n, Hm,
                                       ldh, &one, Fm, (int)n));
         count_launch(c);
-    }
-
-    // Cm(rows x b, ld ldc) = W^T Fm with W = V[:, 0:rows); when Hk != nullptr, Hk (ld ncv) is assigned
-    // (first pass) or incremented (correction passes) by the same coefficients.
-    template <int BP>
-    void wtf_t(int rows, int cols, const float *Fm, float *Cm, int ldc, float *Hk, bool assign)
-    {
-        const int chunks = (int)((n + kWtfChunk - 1) / kWtfChunk);
-        dim3 g((rows + kWtfCols - 1) / kWtfCols, chunks);
-        wtf_partial_kernel<BP><<<g, 256, 0, c.stream>>>(V.p, Fm, n, rows, cols, wpart.p);
-        wtf_reduce_kernel<BP><<<(rows * BP * 32 + 255) / 256, 256, 0, c.stream>>>(wpart.p, chunks, rows, cols, Cm, ldc, Hk,
-                                                                                   ncv, assign ? 1 : 0);
-        count_launch(c, 2);
-    }
-    template <int BP>
-    void fsub_t(int rows, int cols, const float *Cm, int ldc, float *Fm)
-    {
-        fsub_kernel<BP><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(V.p, Cm, ldc, n, rows, cols, Fm);
-        count_launch(c);
-    }
-    void wtf(int rows, int cols, const float *Fm, float *Cm, int ldc, float *Hk, bool assign)
-    {
-        if (cols <= 4) wtf_t<4>(rows, cols, Fm, Cm, ldc, Hk, assign);
-        else if (cols <= 8) wtf_t<8>(rows, cols, Fm, Cm, ldc, Hk, assign);
-        else if (cols <= 12) wtf_t<12>(rows, cols, Fm, Cm, ldc, Hk, assign);
-        else wtf_t<16>(rows, cols, Fm, Cm, ldc, Hk, assign);
-    }
-    void fsub(int rows, int cols, const float *Cm, int ldc, float *Fm)
-    {
-        if (cols <= 4) fsub_t<4>(rows, cols, Cm, ldc, Fm);
-        else if (cols <= 8) fsub_t<8>(rows, cols, Cm, ldc, Fm);
-        else if (cols <= 12) fsub_t<12>(rows, cols, Cm, ldc, Fm);
-        else fsub_t<16>(rows, cols, Cm, ldc, Fm);
     }
 
     // Orthogonalised random refill of V[:, nvecs:target)  (restarted_block_ks.h:106-131, 238-258)
@@ -753,11 +867,17 @@ struct KsState {
             {
                 StatScope s(c, "ks_orth", 2.0 * gs_passes * (double)n * rows * 4.0, 4.0 * gs_passes * (double)n * rows * b);
                 float *Hk = Hat(0, cols);
-                if (custom_orth) {
+                if (custom_orth && panel_tc && rows >= panel_tc_min_rows) {
+                    ptc.split_F(c, F.p, b);
+                    for (int pass = 0; pass < gs_passes; ++pass) {
+                        ptc.wtf(c, V.p, rows, b, C.p, ncv, Hk, ncv, pass == 0);
+                        ptc.fsub(c, V.p, rows, b, F.p);
+                    }
+                } else if (custom_orth) {
                     // Hk = W^T F ; F -= W Hk ; then (gs_passes - 1) x { Ck = W^T F ; F -= W Ck ; Hk += Ck }
                     for (int pass = 0; pass < gs_passes; ++pass) {
-                        wtf(rows, b, F.p, C.p, ncv, Hk, pass == 0);
-                        fsub(rows, b, C.p, ncv, F.p);
+                        ps.wtf(V.p, rows, b, F.p, C.p, ncv, Hk, pass == 0);
+                        ps.fsub(V.p, rows, b, C.p, ncv, F.p);
                     }
                 } else {
                     gemm_tn(rows, b, V.p, F.p, Hk, ncv);                      // Hk = W^T F
@@ -903,6 +1023,35 @@ void block_ks(Ctx &c, uint64_t k64, int b, int max_restarts, float tol, uint64_t
     c.have_P = false;
     if (nconv_out) *nconv_out = nconv;
     if (nconv != k) throw Error(ISLE_ERR_NOCONV, "block_ks: only " + std::to_string(nconv) + " of " + std::to_string(k) + " eigenpairs converged");
+}
+
+// Harness: one C = W^T F, F -= W C pair on caller data with a chosen engine (0 = fp32 FMA scalar loads,
+// 1 = fp32 FMA vector loads, 2 = tcgen05 split TF32), so the engines can be checked in isolation.
+void panel_products(Ctx &c, int64_t n, int rows, int b, const float *W_host, float *F_host_inout, float *C_host_out, int engine)
+{
+    ISLE_REQUIRE(n >= 1 && rows >= 1 && b >= 1 && b <= kMaxB && W_host && F_host_inout && C_host_out, ISLE_ERR_ARG,
+                 "panel_products: bad arguments");
+    DevBuf<float> W((size_t)n * rows), F((size_t)n * b), C((size_t)rows * b);
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(W.p, W_host, W.bytes(), cudaMemcpyHostToDevice, c.stream));
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(F.p, F_host_inout, F.bytes(), cudaMemcpyHostToDevice, c.stream));
+    if (engine == 2) {
+        ISLE_REQUIRE(PanelTc::usable(n), ISLE_ERR_ARG, "panel_products: the tensor-core engine needs n % 4 == 0");
+        PanelTc ptc;
+        ptc.init(c, n, rows);
+        ptc.split_F(c, F.p, b);
+        ptc.wtf(c, W.p, rows, b, C.p, rows, nullptr, 0, true);
+        ptc.fsub(c, W.p, rows, b, F.p);
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));     // ptc's buffers are released on return
+    } else {
+        PanelSimt ps(c);
+        ps.init(n, rows, engine == 1);
+        ps.wtf(W.p, rows, b, F.p, C.p, rows, nullptr, true);
+        ps.fsub(W.p, rows, b, C.p, rows, F.p);
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    }
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(F_host_inout, F.p, F.bytes(), cudaMemcpyDeviceToHost, c.stream));
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(C_host_out, C.p, C.bytes(), cudaMemcpyDeviceToHost, c.stream));
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }
 
 }  // namespace isle

@@ -24,7 +24,7 @@ static std::string head_diag_text(const Ctx &c)
         const volatile uint32_t *r = d + slot * 5;
         if (r[0] == 0) continue;
         char buf[160];
-        std::snprintf(buf, sizeof(buf), " [spmm_head_kernel wait timed out: code=0x%x block=%u thread=%u a=%u b=%u]", r[0] - 1, r[1],
+        std::snprintf(buf, sizeof(buf), " [tcgen05 kernel wait timed out (0x1xxx = panel_tc, else spmm_head): code=0x%x block=%u thread=%u a=%u b=%u]", r[0] - 1, r[1],
                       r[2], r[3], r[4]);
         out += buf;
     }
@@ -268,6 +268,11 @@ int isle_cuda_lloyd_full(isle_cuda_ctx *h, uint64_t k, float *centers_inout, int
         ISLE_REQUIRE(max_reps >= 1, ISLE_ERR_ARG, "lloyd_full: bad arguments");
         lloyd_full(c, k, centers_inout, max_reps, assign_out, objective_out, iters_out);
     });
+}
+
+int isle_cuda_panel_products(isle_cuda_ctx *h, int64_t n, int rows, int b, const float *W, float *F_inout, float *C_out, int engine)
+{
+    return guarded(h, [&](Ctx &c) { panel_products(c, n, rows, b, W, F_inout, C_out, engine); });
 }
 
 int isle_cuda_assign_projected(isle_cuda_ctx *h, uint64_t k, const float *centers, uint32_t *assign_out)

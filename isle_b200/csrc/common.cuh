@@ -316,9 +316,26 @@ void spmm_head_launch(Ctx &c, int b, const uint4 *bits, uint32_t num_mtiles, uin
                       const __nv_bfloat16 *split, float *out, uint32_t m_valid, bool zero_out, bool force_atomic,
                       cudaStream_t stream);
 
+// ---- panel_tc.cu (tall-skinny panel products of block Gram-Schmidt on tcgen05, split TF32)
+struct PanelTc {
+    int64_t n = 0;
+    int ncv = 0;
+    uint32_t seg = 16;                 // 32-k chunks per accumulation segment (= per partial result)
+    size_t fpitch = 0, cpitch = 0;
+    DevBuf<float> fsplit;              // [32][fpitch]: hi (rows 0-15) / lo (rows 16-31) of the block F, K-major
+    DevBuf<float> csplit;              // [32][cpitch]: hi / lo of the coefficient block C
+    DevBuf<float> part;                // partial results [segments][m][16]
+    void init(Ctx &c, int64_t n, int ncv);
+    static bool usable(int64_t n);
+    void split_F(Ctx &c, const float *F, int b);
+    void wtf(Ctx &c, const float *W, int rows, int b, float *C, int ldc, float *Hk, int ldh, bool assign);
+    void fsub(Ctx &c, const float *W, int rows, int b, float *F);
+};
+
 // ---- blockks.cu
 void block_ks(Ctx &c, uint64_t k, int b, int max_restarts, float tol, uint64_t seed,
               float *evalues_out, float *U_out, int *nconv_out);
+void panel_products(Ctx &c, int64_t n, int rows, int b, const float *W_host, float *F_host_inout, float *C_host_out, int engine);
 
 // ---- kmeans.cu
 void project(Ctx &c);

@@ -225,6 +225,11 @@ dist_simt_kernel(const float *__restrict__ P, const float *__restrict__ d2, uint
 // dist = ((-2 P_d . C_c) + ||C_c||^2) + ||P_d||^2, clamped at 0 (:2112-2126).
 static constexpr int kSkinnyMax = 16;
 
+// Four documents per warp pass: every center value read from shared memory feeds four rows, which keeps the
+// shared-memory traffic (one 16-byte read per center per float4 of P otherwise: 16x the HBM bytes at 16
+// centers) under the HBM rate.
+static constexpr int kSkinnyDocs = 4;
+
 __global__ void __launch_bounds__(256)
 pp_skinny_kernel(const float4 *__restrict__ P, const float *__restrict__ d2, uint32_t DB, uint32_t kp4,
                  const float4 *__restrict__ C, const float *__restrict__ c2, uint32_t ncent, float *__restrict__ min_dist)
@@ -233,35 +238,63 @@ pp_skinny_kernel(const float4 *__restrict__ P, const float *__restrict__ d2, uin
     for (uint32_t i = threadIdx.x; i < ncent * kp4; i += blockDim.x) sC[i] = C[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-    for (; d < DB; d += nw) {
-        float acc[kSkinnyMax];
+    uint32_t d0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kSkinnyDocs;
+    const uint32_t stride = ((gridDim.x * blockDim.x) >> 5) * kSkinnyDocs;
+    for (; d0 < DB; d0 += stride) {
+        float acc[kSkinnyDocs][kSkinnyMax];
 #pragma unroll
-        for (int c = 0; c < kSkinnyMax; ++c) acc[c] = 0.f;
+        for (int r = 0; r < kSkinnyDocs; ++r)
+#pragma unroll
+            for (int c = 0; c < kSkinnyMax; ++c) acc[r][c] = 0.f;
+        const float4 *rowp[kSkinnyDocs];
+#pragma unroll
+        for (int r = 0; r < kSkinnyDocs; ++r) rowp[r] = P + (size_t)min(d0 + r, DB - 1) * kp4;   // clamp: tail rows re-read a valid one
         for (uint32_t col = lane; col < kp4; col += 32) {
-            const float4 p = __ldg(P + (size_t)d * kp4 + col);
+            float4 p[kSkinnyDocs];
+#pragma unroll
+            for (int r = 0; r < kSkinnyDocs; ++r) p[r] = __ldg(rowp[r] + col);
 #pragma unroll
             for (int c = 0; c < kSkinnyMax; ++c) {
                 if ((uint32_t)c < ncent) {
                     const float4 q = sC[(size_t)c * kp4 + col];
-                    acc[c] = fmaf(p.x, q.x, fmaf(p.y, q.y, fmaf(p.z, q.z, fmaf(p.w, q.w, acc[c]))));
+#pragma unroll
+                    for (int r = 0; r < kSkinnyDocs; ++r)
+                        acc[r][c] = fmaf(p[r].x, q.x, fmaf(p[r].y, q.y, fmaf(p[r].z, q.z, fmaf(p[r].w, q.w, acc[r][c]))));
                 }
             }
         }
-        float best = FLT_MAX;
-        const float rd2 = d2[d];
+        // transpose-reduce: 16 partial sums per lane x 32 lanes -> lane l ends with the full sum of center
+        // c(l) = bits 4..1 of l (8 + 4 + 2 + 1 + 1 = 16 shuffles per document instead of 16 x 5)
+        const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+        const uint32_t myc = (b16 ? 8u : 0u) + (b8 ? 4u : 0u) + (b4 ? 2u : 0u) + (b2 ? 1u : 0u);
+        const float myc2 = myc < ncent ? c2[myc] : 0.f;
 #pragma unroll
-        for (int c = 0; c < kSkinnyMax; ++c) {
-            if ((uint32_t)c < ncent) {
-                float v = acc[c];
+        for (int r = 0; r < kSkinnyDocs; ++r) {
+            float v8[8], v4[4], v2[2];
 #pragma unroll
-                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                v = fmaxf(__fadd_rn(__fadd_rn(-2.0f * v, c2[c]), rd2), 0.0f);
-                best = fminf(best, v);
+            for (int j = 0; j < 8; ++j) {
+                const float keep = b16 ? acc[r][8 + j] : acc[r][j], send = b16 ? acc[r][j] : acc[r][8 + j];
+                v8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float keep = b8 ? v8[4 + j] : v8[j], send = b8 ? v8[j] : v8[4 + j];
+                v4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float keep = b4 ? v4[2 + j] : v4[j], send = b4 ? v4[j] : v4[2 + j];
+                v2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            float v = (b2 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? v2[0] : v2[1], 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            const uint32_t d = d0 + r;
+            const float rd2 = d < DB ? d2[d] : 0.f;
+            float best = myc < ncent ? fmaxf(__fadd_rn(__fadd_rn(-2.0f * v, myc2), rd2), 0.0f) : FLT_MAX;
+#pragma unroll
+            for (int o = 16; o > 1; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (lane == 0 && d < DB) min_dist[d] = fminf(min_dist[d], best);
         }
-        if (lane == 0) min_dist[d] = fminf(min_dist[d], best);
     }
 }
 
@@ -286,7 +319,7 @@ static void distance_pass(Ctx &c, const float *C, const float *c2, uint32_t ncen
     // engine: 1 = tcgen05 split-TF32 (dist_tc.cu), 0 = SIMT fp32.  Skinny k-means++ updates (a handful of
     // new centers) are a memory-bound pass over P and stay on the SIMT engine, which reads P once.
     const bool tc = c.opt("dist_kernel", 1) == 1 && dist_tc_supported(c, kp, ncent) &&
-                    (mode == 0 || (int)ncent >= c.opt("dist_tc_min_centers", 32));
+                    (mode == 0 || (int)ncent >= c.opt("dist_tc_min_centers", kSkinnyMax + 1));
     const size_t skinny_smem = (size_t)ncent * kp * sizeof(float);
     const bool skinny = mode == 1 && !tc && ncent <= (uint32_t)kSkinnyMax && skinny_smem <= 160 * 1024 &&
                         c.opt("pp_skinny", 1) != 0;
@@ -296,7 +329,7 @@ static void distance_pass(Ctx &c, const float *C, const float *c2, uint32_t ncen
     if (skinny) {
         ISLE_CUDA_CHECK(cudaFuncSetAttribute(pp_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skinny_smem));
         const unsigned per_sm = skinny_smem > 100 * 1024 ? 1u : 2u;
-        pp_skinny_kernel<<<std::min<unsigned>((DB + 7) / 8, (unsigned)c.num_sms * per_sm * 4), 256, skinny_smem, c.stream>>>(
+        pp_skinny_kernel<<<std::min<unsigned>((DB + 8 * kSkinnyDocs - 1) / (8 * kSkinnyDocs), (unsigned)c.num_sms * per_sm * 4), 256, skinny_smem, c.stream>>>(
             reinterpret_cast<const float4 *>(c.P.p), c.p_l2.p, DB, kp / 4, reinterpret_cast<const float4 *>(C), c2, ncent, min_dist);
         ISLE_CUDA_CHECK(cudaGetLastError());
         count_launch(c);

@@ -230,6 +230,45 @@ def test_block_ks_c1(ctx, golden_c1, corpus_c1):
     check_eigs(ev, U, g["evalues"], g["U_colmajor"].reshape(c.k, c.V).T, float(g["frobenius"]))
 
 
+@pytest.mark.parametrize("engine", [0, 1, 2], ids=["fma-scalar", "fma-vector", "tcgen05"])
+@pytest.mark.parametrize("shape", [(600, 20, 10), (1000, 7, 3), (4096, 130, 16), (20004, 129, 1), (20000, 300, 10)])
+def test_panel_product_engines(ctx, engine, shape):
+    """One block Gram-Schmidt pass (restarted_block_ks.h:83-84), C = W^T F and F -= W C, on random
+    orthonormal W against float64: every engine of the device solver, ragged shapes included."""
+    from isle_b200._capi import ptr
+    n, rows, b = shape
+    rng = np.random.default_rng(n + rows + b)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, rows)))
+    W = Q.astype(np.float32)
+    F = (rng.standard_normal((n, b)) * np.logspace(0, -3, b)[None, :]).astype(np.float32)   # columns of very different scale
+    Wc, Fc, Cc = np.ascontiguousarray(W.T), F.T.copy(), np.zeros((b, rows), np.float32)     # copy: F.T aliases F when b = 1
+    ctx.call("isle_cuda_panel_products", n, rows, b, ptr(Wc), ptr(Fc), ptr(Cc), engine)
+    fn = np.linalg.norm(F.astype(np.float64), axis=0)
+    C_ref = W.astype(np.float64).T @ F.astype(np.float64)
+    assert np.max(np.abs(Cc.T - C_ref) / fn[None, :]) < 2e-6
+    F_ref = F.astype(np.float64) - W.astype(np.float64) @ Cc.T.astype(np.float64)
+    assert np.max(np.abs(Fc.T - F_ref) / fn[None, :]) < 2e-6
+
+
+@pytest.mark.parametrize("opts", [dict(ks_panel_tc=0, ks_panel_v2=0), dict(ks_panel_tc=0, ks_panel_v2=1), dict(ks_panel_tc=1),
+                                  dict(ks_panel_tc=0, ks_panel_v2=0, ks_custom_orth=0, ks_fast_qr=0)],
+                         ids=["scalar-panels", "vector-panels", "tcgen05-panels", "cublas-mgs"])
+def test_block_ks_engine_variants_c1(ctx, golden_c1, corpus_c1, opts):
+    """Every panel / QR engine of the device solver meets the same bar against the reference's output."""
+    g, c = golden_c1, corpus_c1
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    A, B, *_ = make_AB(ctx, c.V, c.D, c.k, vals, c.rows, c.offsets, avg, nz)
+    defaults = dict(ks_panel_tc=1, ks_panel_v2=1, ks_custom_orth=1, ks_fast_qr=1)
+    try:
+        for k_, v_ in {**defaults, **opts}.items():
+            ctx.set_option(k_, v_)
+        ev, U = B.compute_block_ks(c.k, seed=3, want_U=True)
+    finally:
+        for k_, v_ in defaults.items():
+            ctx.set_option(k_, v_)
+    check_eigs(ev, U, g["evalues"], g["U_colmajor"].reshape(c.k, c.V).T, float(g["frobenius"]))
+
+
 def test_block_ks_rejects_bad_k(ctx, golden_tiny):
     from isle_b200._capi import IsleCudaError
     A, B, *_ = tiny_AB(ctx, golden_tiny)
@@ -389,7 +428,8 @@ def test_lloyd_full_from_device_resident_lifted_centers(ctx, golden_tiny):
     C = np.ascontiguousarray(lifted.T.copy())
     B.run_lloyds(k, C, None, 10)
     assert np.array_equal(dev["assign"], B.last_lloyd_full["assign"])
-    assert dev["iters"] == B.last_lloyd_full["iters"] and dev["objective"] == B.last_lloyd_full["objective"]
+    assert dev["iters"] == B.last_lloyd_full["iters"]
+    assert abs(dev["objective"] - B.last_lloyd_full["objective"]) <= 1e-12 * dev["objective"]   # fp64 atomics: order varies
 
 
 # ---------------------------------------------------------------- end to end
