@@ -329,7 +329,7 @@ def bench_ours(args):
     dev_ms = ms.value
     st = {n: ctx.stat(n) for n in ("launches", "spmm_bt_ms", "spmm_bt_bytes", "spmm_bt_calls", "spmm_b_ms",
                                    "spmm_b_bytes", "spmm_b_calls", "ks_op_ms", "ks_orth_ms", "ks_qr_ms",
-                                   "ks_truncate_ms", "ks_restarts", "project_ms", "lloyd_iter_ms", "pp_round_ms",
+                                   "ks_truncate_ms", "ks_restarts", "ks_gs_elided", "ks_ops", "project_ms", "lloyd_iter_ms", "pp_round_ms",
                                    "thr_hist_ms", "thr_zeta_ms", "b_count_ms", "b_compact_ms", "csr_build_ms",
                                    "dist_tc_ms", "dist_simt_ms", "dist_tc_flops", "dist_simt_flops", "lloyd_accum_ms",
                                    "ks_wtf_ms", "ks_wtf_bytes", "ks_wtfred_ms", "ks_fsub_ms", "ks_fsub_bytes", "pp_dist_tc_ms",
@@ -381,6 +381,7 @@ def bench_ours(args):
             "config": {"workload": f"{args.config} {SHAPES.get(args.config, 'synthetic')} per GPU: {D} docs x {V} vocab, {nnz} nnz, k={k}",
                        "block_size": 10, "tol": 1e-4, "l2": "inputs (A: %.0f MB) larger than the 126 MB L2" % (nnz * 8 / 1e6),
                        "D_B": state["DB"], "nnz_B": state["nnzB"], "ks_restarts": st["ks_restarts"],
+                       "ks_block_steps": st["ks_ops"], "ks_gs_third_passes_elided": st["ks_gs_elided"],
                        "spmm_head_words": int(st["spmm_head_words"]), "spmm_tail_nnz": int(st["spmm_tail_nnz"]),
                        "lloyd_iters": state["iters"], "nconv": state["nconv"]},
             "e2e": {"value": total_docs * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -394,8 +395,12 @@ def bench_ours(args):
                          "avg_launch_ms": spmm_ms / ncalls if ncalls else None,
                          "bytes_per_launch": spmm_bytes / ncalls if ncalls else None},
             "stage_ms_per_step": {n[:-3]: st[n] / args.steps for n in st if n.endswith("_ms")},
-            "panel_gbs": {"wtf": st["ks_wtf_bytes"] / st["ks_wtf_ms"] / 1e6 if st["ks_wtf_ms"] else None,
-                          "fsub": st["ks_fsub_bytes"] / st["ks_fsub_ms"] / 1e6 if st["ks_fsub_ms"] else None},
+            # block Gram-Schmidt panel products: algorithmic bytes (n x rows x 4 per product) of the passes that ran
+            # (elided third passes return at once and move nothing) / CUDA-event time, reduce kernels included
+            "panel_gbs": (lambda live: {"wtf": live * st["ks_wtf_bytes"] / st["ks_wtf_ms"] / 1e6 if st["ks_wtf_ms"] else None,
+                                        "fsub": live * st["ks_fsub_bytes"] / st["ks_fsub_ms"] / 1e6 if st["ks_fsub_ms"] else None,
+                                        "passes_run_fraction": live})(
+                1.0 - (st["ks_gs_elided"] * args.steps) / max(3.0 * st["ks_ops"], 1.0)),
             "step_wall_ms": [round(x, 2) for x in step_wall],
             "next_rows": {"lloyd_full": {"what": "SURVEY 8(f) row 1: run_lloyds on the full-dimensional B (trainer.cpp:566), "
                                                  "device-resident, not part of the metric", "ms": fms.value, "iters": fit.value,

@@ -247,38 +247,59 @@ struct CholQrParams {
     double *part;        // gridDim.x x 256 partial Gram sums
 };
 
-// Gram partials of this block's rows of X = F * T (T upper triangular b x b in smem, or
-// identity when T == nullptr).  Thread (p = tid & 15, r = tid >> 4) owns row r of each
-// 16-row tile and column p of the Gram matrix.
+// Gram partials of this block's rows of X = F * T (T upper triangular b x b in smem, or identity when
+// T == nullptr).  The CTA walks 64-row tiles: loads are coalesced (thread = row (tid & 63) of the tile, columns
+// tid >> 6 + {0, 4, 8, 12}: a warp reads 32 consecutive rows of one column) and the next tile is prefetched
+// into registers while this one is reduced; in the reduction thread (p = tid & 15, r = tid >> 4) owns rows
+// r, r + 16, r + 32, r + 48 of the tile and column p of the Gram matrix.
+static constexpr int kCholTile = 64;
+
 __device__ __forceinline__ void gram_partial(const CholQrParams &p, const double (*T)[kMaxB], double (*xs)[kMaxB + 1],
                                              double (*ys)[kMaxB + 1], double *red, double *dst)
 {
     const int pc = threadIdx.x & 15, r = threadIdx.x >> 4;
+    const int lrow = threadIdx.x & (kCholTile - 1), lcg = threadIdx.x >> 6;
     const int b = p.b;
     double acc[kMaxB];
 #pragma unroll
     for (int q = 0; q < kMaxB; ++q) acc[q] = 0.0;
-    const int64_t step = (int64_t)gridDim.x * 16;
-    int64_t row0 = (int64_t)blockIdx.x * 16;
-    float nxt = (row0 + r < p.n && pc < b) ? p.F[row0 + r + (size_t)pc * p.n] : 0.f;
+    const int64_t step = (int64_t)gridDim.x * kCholTile;
+    int64_t row0 = (int64_t)blockIdx.x * kCholTile;
+    float nxt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int col = lcg + 4 * u;
+        nxt[u] = (row0 + lrow < p.n && col < b) ? p.F[row0 + lrow + (size_t)col * p.n] : 0.f;
+    }
     for (; row0 < p.n; row0 += step) {
-        xs[r][pc] = (double)nxt;
-        {   // prefetch the next tile's element while this one is reduced
-            const int64_t rown = row0 + step + r;
-            nxt = (rown < p.n && pc < b) ? p.F[rown + (size_t)pc * p.n] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xs[lrow][lcg + 4 * u] = (double)nxt[u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {   // prefetch the next tile while this one is reduced
+            const int col = lcg + 4 * u;
+            const int64_t rown = row0 + step + lrow;
+            nxt[u] = (rown < p.n && col < b) ? p.F[rown + (size_t)col * p.n] : 0.f;
         }
         __syncthreads();
         double (*src)[kMaxB + 1] = xs;
         if (T) {
-            double y = 0.0;
-            for (int i = 0; i <= pc; ++i) y += xs[r][i] * T[i][pc];
-            ys[r][pc] = (pc < b) ? y : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rr = r + 16 * u;
+                double y = 0.0;
+                for (int i = 0; i <= pc; ++i) y += xs[rr][i] * T[i][pc];
+                ys[rr][pc] = (pc < b) ? y : 0.0;
+            }
             __syncthreads();
             src = ys;
         }
-        const double mine = src[r][pc];
 #pragma unroll
-        for (int q = 0; q < kMaxB; ++q) acc[q] += mine * src[r][q];
+        for (int u = 0; u < 4; ++u) {
+            const int rr = r + 16 * u;
+            const double mine = src[rr][pc];
+#pragma unroll
+            for (int q = 0; q < kMaxB; ++q) acc[q] += mine * src[rr][q];
+        }
         __syncthreads();
     }
     // reduce over the 16 row-owners r in a fixed order
@@ -353,7 +374,7 @@ __global__ void __launch_bounds__(256)
 cholqr2_kernel(CholQrParams p)
 {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double xs[16][kMaxB + 1], ys[16][kMaxB + 1];
+    __shared__ double xs[kCholTile][kMaxB + 1], ys[kCholTile][kMaxB + 1];
     __shared__ double G[256];
     __shared__ double R1[kMaxB][kMaxB], R1i[kMaxB][kMaxB], R2[kMaxB][kMaxB], R2i[kMaxB][kMaxB], T[kMaxB][kMaxB];
     __shared__ int s_ok;
@@ -382,15 +403,24 @@ cholqr2_kernel(CholQrParams p)
         if (blockIdx.x == 0 && i < b && j < b) p.R[i + (size_t)j * b] = (float)rr;
     }
     __syncthreads();
-    const int pc = threadIdx.x & 15, r = threadIdx.x >> 4;
-    for (int64_t row0 = (int64_t)blockIdx.x * 16; row0 < p.n; row0 += (int64_t)gridDim.x * 16) {
-        const int64_t row = row0 + r;
-        xs[r][pc] = (row < p.n && pc < b) ? (double)p.F[row + (size_t)pc * p.n] : 0.0;
+    // Q = F T: same 64-row tiles, coalesced loads and stores (thread = row of the tile, four columns each)
+    const int lrow = threadIdx.x & (kCholTile - 1), lcg = threadIdx.x >> 6;
+    for (int64_t row0 = (int64_t)blockIdx.x * kCholTile; row0 < p.n; row0 += (int64_t)gridDim.x * kCholTile) {
+        const int64_t row = row0 + lrow;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int col = lcg + 4 * u;
+            xs[lrow][col] = (row < p.n && col < b) ? (double)p.F[row + (size_t)col * p.n] : 0.0;
+        }
         __syncthreads();
-        if (row < p.n && pc < b) {
-            double y = 0.0;
-            for (int i = 0; i <= pc; ++i) y += xs[r][i] * T[i][pc];
-            p.Q[row + (size_t)pc * p.n] = (float)y;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int col = lcg + 4 * u;
+            if (row < p.n && col < b) {
+                double y = 0.0;
+                for (int i = 0; i <= col; ++i) y += xs[lrow][i] * T[i][col];
+                p.Q[row + (size_t)col * p.n] = (float)y;
+            }
         }
         __syncthreads();
     }
@@ -697,6 +727,7 @@ struct KsState {
     int chol_grid = 1, gs_passes = 3;
     bool fast_qr = true, custom_orth = true, panel_v2 = true, panel_tc = true;
     int panel_tc_min_rows = 0;
+    bool gs_elide = true;
     PanelTc ptc;
     DevBuf<int> drank, dinfo;
     int lwork = 0;
@@ -739,7 +770,7 @@ struct KsState {
         ISLE_CUDA_CHECK(cudaFuncSetAttribute(cholqr2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholDynSmem));
         ISLE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cholqr2_kernel, 256, kCholDynSmem));
         ISLE_REQUIRE(per_sm >= 1, ISLE_ERR_CUDA, "cholqr2_kernel cannot be made resident");
-        chol_grid = std::max(1, std::min((int)((n + 15) / 16), c.num_sms));   // every CTA re-sums all partials: keep them few
+        chol_grid = std::max(1, std::min((int)((n + kCholTile - 1) / kCholTile), c.num_sms));   // every CTA re-sums all partials: keep them few
         cpart.alloc((size_t)2 * chol_grid * 256);
         fast_qr = c.opt("ks_fast_qr", 1) != 0;
         custom_orth = c.opt("ks_custom_orth", 1) != 0;
@@ -749,6 +780,7 @@ struct KsState {
         panel_tc = c.opt("ks_panel_tc", 1) != 0 && PanelTc::usable(n) && b <= 16;
         panel_tc_min_rows = c.opt("ks_panel_tc_min_rows", 0);
         if (panel_tc) ptc.init(c, n, ncv);
+        gs_elide = c.opt("ks_gs_elide", 1) != 0;
         gs_passes = std::max(2, std::min(3, c.opt("ks_gs_passes", 3)));
     }
 
@@ -868,10 +900,15 @@ struct KsState {
                 StatScope s(c, "ks_orth", 2.0 * gs_passes * (double)n * rows * 4.0, 4.0 * gs_passes * (double)n * rows * b);
                 float *Hk = Hat(0, cols);
                 if (custom_orth && panel_tc && rows >= panel_tc_min_rows) {
+                    // The reference always runs three passes (restarted_block_ks.h:83-90).  When the second pass only
+                    // moved coefficients below 1e-4 of the first's, what is left along W is below fp32 resolution
+                    // of H and the third pass is elided on the device (no host round trip; ks_gs_elide = 0 keeps it).
+                    ptc.begin_step(c);
                     ptc.split_F(c, F.p, b);
                     for (int pass = 0; pass < gs_passes; ++pass) {
-                        ptc.wtf(c, V.p, rows, b, C.p, ncv, Hk, ncv, pass == 0);
-                        ptc.fsub(c, V.p, rows, b, F.p);
+                        ptc.wtf(c, V.p, rows, b, C.p, ncv, Hk, ncv, pass == 0, gs_elide ? pass : 0);
+                        ptc.fsub(c, V.p, rows, b, F.p, gs_elide ? pass : 0);
+                        if (gs_elide && pass == 1 && gs_passes > 2) ptc.decide_elision(c, 1e-4f);
                     }
                 } else if (custom_orth) {
                     // Hk = W^T F ; F -= W Hk ; then (gs_passes - 1) x { Ck = W^T F ; F -= W Ck ; Hk += Ck }
@@ -1008,6 +1045,7 @@ void block_ks(Ctx &c, uint64_t k64, int b, int max_restarts, float tol, uint64_t
     }
     nconv = std::min(nconv, k);
     c.counters["ks_restarts"] = n_restarts;
+    c.counters["ks_gs_elided"] = ks.panel_tc ? (double)ks.ptc.elided(c) : 0.0;
     c.counters["ks_nconv"] = nconv;
 
     // src/sparseMatrix.cpp:1209-1214: eigenvalues = diag(H)[0:k], eigenvectors = V[:, 0:k)

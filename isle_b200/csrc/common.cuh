@@ -325,11 +325,17 @@ struct PanelTc {
     DevBuf<float> fsplit;              // [32][fpitch]: hi (rows 0-15) / lo (rows 16-31) of the block F, K-major
     DevBuf<float> csplit;              // [32][cpitch]: hi / lo of the coefficient block C
     DevBuf<float> part;                // partial results [segments][m][16]
+    DevBuf<uint32_t> flags;            // largest |coefficient| of pass 0 / 1 (bit patterns), skip flag, elided-pass counter
     void init(Ctx &c, int64_t n, int ncv);
     static bool usable(int64_t n);
+    void begin_step(Ctx &c);
     void split_F(Ctx &c, const float *F, int b);
-    void wtf(Ctx &c, const float *W, int rows, int b, float *C, int ldc, float *Hk, int ldh, bool assign);
-    void fsub(Ctx &c, const float *W, int rows, int b, float *F);
+    // pass = index of the Gram-Schmidt pass inside the block step (0, 1 record their largest coefficient;
+    // passes >= 2 return at once when decide_elision() set the skip flag)
+    void wtf(Ctx &c, const float *W, int rows, int b, float *C, int ldc, float *Hk, int ldh, bool assign, int pass = 0);
+    void fsub(Ctx &c, const float *W, int rows, int b, float *F, int pass = 0);
+    void decide_elision(Ctx &c, float ratio);
+    uint32_t elided(Ctx &c);
 };
 
 // ---- blockks.cu

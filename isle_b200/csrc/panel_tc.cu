@@ -199,12 +199,14 @@ struct PanelParams {
     uint32_t nseg;         // K segments = ceil(NC / seg)
     uint32_t stages;
     uint32_t *diag;
+    const uint32_t *skip;  // device flag: non-zero = this launch is an elided Gram-Schmidt pass, return at once
 };
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 panel_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const PanelParams p)
 {
+    if (p.skip && *reinterpret_cast<const volatile uint32_t *>(p.skip)) return;    // uniform: before any barrier or TMEM allocation
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *ctrl = smem + (size_t)p.stages * kStageBytes;
@@ -440,8 +442,10 @@ split_operand_kernel(const float *__restrict__ X, size_t ld, uint32_t len, uint3
 // csplit rows c / 16 + c = hi / lo of the value (operand of the F -= W C product that follows).  One warp per (j, c).
 __global__ void __launch_bounds__(256)
 wtf_reduce_tc_kernel(const float *__restrict__ partial, int nseg, int rows, int b, float *__restrict__ C, int ldc,
-                     float *__restrict__ Hk, int ldh, int hk_assign, float *__restrict__ csplit, size_t cpitch)
+                     float *__restrict__ Hk, int ldh, int hk_assign, float *__restrict__ csplit, size_t cpitch,
+                     uint32_t *__restrict__ cmax_bits, const uint32_t *__restrict__ skip)
 {
+    if (skip && *skip) return;
     const int lane = threadIdx.x & 31;
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= rows * 16) return;
@@ -457,14 +461,29 @@ wtf_reduce_tc_kernel(const float *__restrict__ partial, int nseg, int rows, int 
         const float hi = __uint_as_float(tf32_rna(v));
         csplit[(size_t)c * cpitch + j] = hi;
         csplit[(size_t)(16 + c) * cpitch + j] = v - hi;
+        // largest coefficient of this pass (bit patterns of non-negative floats order like integers: the
+        // maximum is independent of the order of the atomics, so replicated ranks decide identically)
+        if (cmax_bits) atomicMax(cmax_bits, __float_as_uint(fabsf(v)) & 0x7FFFFFFFu);
     }
+}
+
+// skip = 1 when the pass just finished only moved coefficients below `ratio` of the first pass's (they are then
+// below fp32 resolution of H and a further pass cannot improve the orthogonality); counts the elisions
+__global__ void gs_decide_kernel(const uint32_t *__restrict__ cmax_bits, float ratio, uint32_t *__restrict__ skip,
+                                 uint32_t *__restrict__ elided)
+{
+    const float c1 = __uint_as_float(cmax_bits[0]), c2 = __uint_as_float(cmax_bits[1]);
+    const uint32_t s = (c2 <= ratio * c1 && isfinite(c1) && isfinite(c2)) ? 1u : 0u;
+    *skip = s;
+    *elided += s;
 }
 
 // F[i + c n] -= sum over segments of delta[s][i][c] (fixed order); fsplit = hi / lo of the new F (operand of the next W^T F)
 __global__ void __launch_bounds__(256)
 fsub_reduce_tc_kernel(const float4 *__restrict__ delta, int nseg, uint32_t n, int b, float *__restrict__ F, float *__restrict__ fsplit,
-                      size_t fpitch)
+                      size_t fpitch, const uint32_t *__restrict__ skip)
 {
+    if (skip && *skip) return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float v[16];
@@ -526,6 +545,29 @@ void PanelTc::init(Ctx &c, int64_t n_, int ncv_)
     const size_t nseg_w = ((size_t)(n + kKC - 1) / kKC + seg - 1) / seg;          // W^T F: K = n
     const size_t nseg_f = ((size_t)(ncv + kKC - 1) / kKC + seg - 1) / seg;        // F -= W C: K <= ncv
     part.alloc(std::max(nseg_w * (size_t)ncv, nseg_f * (size_t)n) * 16);
+    flags.alloc(4);        // [0], [1]: largest |coefficient| of the first / the latest pass; [2]: skip flag; [3]: elided passes
+    ISLE_CUDA_CHECK(cudaMemsetAsync(flags.p, 0, flags.bytes(), c.stream));
+}
+
+// Start of a block step: no pass elided yet.
+void PanelTc::begin_step(Ctx &c)
+{
+    ISLE_CUDA_CHECK(cudaMemsetAsync(flags.p, 0, 3 * sizeof(uint32_t), c.stream));
+}
+
+// After the second pass: elide what follows when its coefficients were below `ratio` of the first pass's.
+void PanelTc::decide_elision(Ctx &c, float ratio)
+{
+    gs_decide_kernel<<<1, 1, 0, c.stream>>>(flags.p, ratio, flags.p + 2, flags.p + 3);
+    count_launch(c);
+}
+
+uint32_t PanelTc::elided(Ctx &c)
+{
+    uint32_t v = 0;
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(&v, flags.p + 3, 4, cudaMemcpyDeviceToHost, c.stream));
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    return v;
 }
 
 bool PanelTc::usable(int64_t n_) { return n_ % 4 == 0; }   // TMA needs 16-byte global strides
@@ -539,9 +581,11 @@ void PanelTc::split_F(Ctx &c, const float *F, int b)
 
 // C(rows x b, ld ldc) = W^T F with W = V[:, 0:rows) (ld n) and F as last split; Hk (ld ldh) assigned or incremented;
 // leaves csplit = hi / lo of C for the F -= W C that follows.
-void PanelTc::wtf(Ctx &c, const float *W, int rows, int b, float *C, int ldc, float *Hk, int ldh, bool assign)
+void PanelTc::wtf(Ctx &c, const float *W, int rows, int b, float *C, int ldc, float *Hk, int ldh, bool assign, int pass)
 {
     PanelParams p{};
+    p.skip = pass >= 2 ? flags.p + 2 : nullptr;
+    uint32_t *cmax = pass == 0 ? flags.p : (pass == 1 ? flags.p + 1 : nullptr);
     p.out = part.p;
     p.m_total = (uint32_t)rows;
     p.num_mtiles = (uint32_t)(rows + 127) / 128;
@@ -560,15 +604,16 @@ void PanelTc::wtf(Ctx &c, const float *W, int rows, int b, float *C, int ldc, fl
         // stale csplit columns of an earlier, wider call cannot matter: the W tile is zero beyond `rows`
         // and csplit only ever holds finite values
         wtf_reduce_tc_kernel<<<(unsigned)(((size_t)rows * 16 * 32 + 255) / 256), 256, 0, c.stream>>>(
-            part.p, (int)p.nseg, rows, b, C, ldc, Hk, ldh, assign ? 1 : 0, csplit.p, cpitch);
+            part.p, (int)p.nseg, rows, b, C, ldc, Hk, ldh, assign ? 1 : 0, csplit.p, cpitch, cmax, p.skip);
         count_launch(c);
     }
 }
 
 // F -= W C with C as left in csplit by wtf(); leaves fsplit = hi / lo of the new F.
-void PanelTc::fsub(Ctx &c, const float *W, int rows, int b, float *F)
+void PanelTc::fsub(Ctx &c, const float *W, int rows, int b, float *F, int pass)
 {
     PanelParams p{};
+    p.skip = pass >= 2 ? flags.p + 2 : nullptr;
     p.out = part.p;
     p.m_total = (uint32_t)n;
     p.num_mtiles = (uint32_t)((n + 127) / 128);
@@ -582,7 +627,7 @@ void PanelTc::fsub(Ctx &c, const float *W, int rows, int b, float *F)
         StatScope s(c, "ks_fsub", (double)n * rows * 4.0, 2.0 * (double)n * rows * b);
         launch_panel<1>(c, ma, mb, p);
         fsub_reduce_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(reinterpret_cast<const float4 *>(part.p), (int)p.nseg,
-                                                                                (uint32_t)n, b, F, fsplit.p, fpitch);
+                                                                                (uint32_t)n, b, F, fsplit.p, fpitch, p.skip);
         count_launch(c);
     }
 }

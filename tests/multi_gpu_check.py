@@ -8,7 +8,8 @@ Every rank holds a contiguous slice of the documents; the library exchanges per-
 the V x b operator blocks, k-means++ picks and Lloyd center sums over NCCL.  Every rank then
 repeats the computation alone on the whole corpus (world = 1 context on its own GPU) and checks:
 thresholds and its slice of B bit-exact, singular values within 1e-4 relative, principal angle
-below 1e-3, Lloyd objective within 1e-4 from identical initial centers.
+below 1e-3, Lloyd objective within 1e-4 from identical initial centers, and the full-dimensional Lloyd
+(stage F) bit-identical from identical centers (its sharded reduction is integer).
 """
 import os
 import sys
@@ -25,7 +26,7 @@ from isle_b200.sparse_matrix import FPSparseMatrix, SparseMatrix  # noqa: E402
 from oracle import isle_oracle as O  # noqa: E402  (checker only)
 
 
-def stages(ctx, V, D, k, vals, rows, offsets, avg, nz, centers0=None, U_override=None, seed=3):
+def stages(ctx, V, D, k, vals, rows, offsets, avg, nz, centers0=None, U_override=None, seed=3, full_centers0=None):
     A = SparseMatrix(V, D, ctx)
     A.populate_normalized(vals, rows, offsets, avg, nz)
     z, nn = A.compute_thresholds(0, V, None, k)
@@ -38,8 +39,18 @@ def stages(ctx, V, D, k, vals, rows, offsets, avg, nz, centers0=None, U_override
     seeds, coords, res = B.kmeans_init_on_projected_space(k, 1, seed=seed)
     c0 = coords.copy() if centers0 is None else centers0.copy()
     B.run_lloyds_on_projected_space(k, c0, None, 10)
+    # stage F: lift, clean up, Lloyd on the full-dimensional B from given centers
+    if full_centers0 is None:
+        full = np.ascontiguousarray(B.left_multiply_by_U_Spectra(c0, k, k).T)
+    else:
+        full = full_centers0.copy()
+    full_in = full.copy()
+    B.cleanup_after_eigensolver()
+    B.run_lloyds(k, full, None, 10)
     return dict(z=z, nn=nn, bv=bv, br=br, bo=bo, oc=oc, ev=ev, U=U, seeds=seeds, coords=coords, centers=c0,
-                obj=B.last_lloyd["objective"], assign=B.last_lloyd["assign"], iters=B.last_lloyd["iters"])
+                obj=B.last_lloyd["objective"], assign=B.last_lloyd["assign"], iters=B.last_lloyd["iters"],
+                full_in=full_in, full=full, full_obj=B.last_lloyd_full["objective"], full_assign=B.last_lloyd_full["assign"],
+                full_iters=B.last_lloyd_full["iters"])
 
 
 def main():
@@ -63,7 +74,8 @@ def main():
     # the single-GPU run; its k-means stages get the sharded run's U and k-means++ centers so that
     # both Lloyd runs see the same projection and start identically
     one = _capi.Context(local)
-    s = stages(one, c.V, c.D, c.k, vals, c.rows, c.offsets, float(avg), nz, centers0=r["coords"], U_override=r["U"])
+    s = stages(one, c.V, c.D, c.k, vals, c.rows, c.offsets, float(avg), nz, centers0=r["coords"], U_override=r["U"],
+               full_centers0=r["full_in"])
 
     ok = True
 
@@ -95,6 +107,12 @@ def main():
         check(mism < 5e-3, f"Lloyd assignments differ on {mism:.2%} of the local docs")
     else:
         mism = 0.0
+    # stage F from identical centers: integer member counts are allreduced, so centers and partition agree exactly
+    check(np.array_equal(r["full"], s["full"]), f"full-dimensional Lloyd centers differ: {np.abs(r['full'] - s['full']).max():.2e}")
+    check(r["full_iters"] == s["full_iters"], "full-dimensional Lloyd iteration counts differ")
+    check(abs(r["full_obj"] - s["full_obj"]) <= 1e-9 * s["full_obj"], "full-dimensional Lloyd objective differs")
+    if len(sel):
+        check(np.array_equal(s["full_assign"][sel], r["full_assign"]), "full-dimensional Lloyd assignments differ")
     # k-means++ seeds are global column ids of B and must be distinct
     check(len(set(r["seeds"].tolist())) == c.k and int(r["seeds"].max()) < len(s["oc"]), "bad k-means++ seeds")
     flag = torch.tensor([0 if ok else 1], device="cuda")
