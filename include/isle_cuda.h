@@ -139,6 +139,24 @@ int isle_cuda_lift_centers(isle_cuda_ctx *ctx, uint64_t ncols, const float *in, 
  * NULL) = iterations executed.  max_reps >= 1. */
 int isle_cuda_lloyd_full(isle_cuda_ctx *ctx, uint64_t k, float *centers_inout, int max_reps,
                          uint32_t *assign_out, double *objective_out, int *iters_out);
+/* SURVEY 8(f) row 2, first half.  Replaces SparseMatrix::rth_highest_element (src/sparseMatrix.cpp:491-524),
+ * which train() calls once per topic (src/trainer.cpp:587-589): thresholds_out[w] (V floats) = the r-th highest
+ * normalised value of word w among the listed documents of A (original ids) when w occurs in MORE than r of
+ * them; otherwise 0, except when r >= ndocs and w occurs in every listed document: then the smallest value.
+ * Bit-identical to the reference (a selection of the uploaded floats).  r >= 1.  Needs isle_cuda_upload_A only. */
+int isle_cuda_rth_highest_element(isle_cuda_ctx *ctx, uint64_t r, const uint64_t *docs, uint64_t ndocs,
+                                  float *thresholds_out);
+/* The same for all k clusters in one pass: cluster_of_doc[d] in [0, k) or 0xFFFFFFFF (document in no cluster) for
+ * the D documents of A; thresholds_out (k x V, topic-major: thresholds[w + t V], the layout of train()'s
+ * catchword_thresholds) may be NULL (result kept on the device for isle_cuda_find_catchwords). */
+int isle_cuda_catchword_thresholds(isle_cuda_ctx *ctx, uint64_t k, uint64_t r, const uint32_t *cluster_of_doc,
+                                   float *thresholds_out);
+/* Replaces SparseMatrix::find_catchwords (src/sparseMatrix.cpp:573-594): topic_of_word_out[w] = the topic t with
+ * thresholds[w + t V] > rho * thresholds[w + o V] for every other topic o (compared in double, as the reference's
+ * expression evaluates), or -1.  At most one topic can qualify when rho >= 1 (rho_c = 1.1, include/hyperparams.h:11).
+ * thresholds: k x V host matrix, or NULL = the device matrix of the last isle_cuda_catchword_thresholds. */
+int isle_cuda_find_catchwords(isle_cuda_ctx *ctx, uint64_t k, const float *thresholds, double rho,
+                              int32_t *topic_of_word_out);
 /* Harness only (no reference counterpart): one block Gram-Schmidt pass of BlockKs::expand
  * (block-ks/restarted_block_ks.h:83-84) on caller data, C = W^T F then F -= W C, with a chosen engine
  * (0 = fp32 FMA, 1 = fp32 FMA with vector loads, 2 = tcgen05 split TF32), so the panel engines of the

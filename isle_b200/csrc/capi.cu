@@ -270,6 +270,21 @@ int isle_cuda_lloyd_full(isle_cuda_ctx *h, uint64_t k, float *centers_inout, int
     });
 }
 
+int isle_cuda_catchword_thresholds(isle_cuda_ctx *h, uint64_t k, uint64_t r, const uint32_t *cluster_of_doc, float *thresholds_out)
+{
+    return guarded(h, [&](Ctx &c) { catchword_thresholds(c, k, r, cluster_of_doc, thresholds_out); });
+}
+
+int isle_cuda_rth_highest_element(isle_cuda_ctx *h, uint64_t r, const uint64_t *docs, uint64_t ndocs, float *thresholds_out)
+{
+    return guarded(h, [&](Ctx &c) { rth_highest_element(c, r, docs, ndocs, thresholds_out); });
+}
+
+int isle_cuda_find_catchwords(isle_cuda_ctx *h, uint64_t k, const float *thresholds, double rho, int32_t *topic_of_word_out)
+{
+    return guarded(h, [&](Ctx &c) { find_catchwords(c, k, thresholds, rho, topic_of_word_out); });
+}
+
 int isle_cuda_panel_products(isle_cuda_ctx *h, int64_t n, int rows, int b, const float *W, float *F_inout, float *C_out, int engine)
 {
     return guarded(h, [&](Ctx &c) { panel_products(c, n, rows, b, W, F_inout, C_out, engine); });

@@ -245,6 +245,8 @@ struct Ctx {
     DevBuf<float> P;                       // DB x kp row-major, zero padded
     DevBuf<float> P_hi, P_lo;              // split-TF32 copies of P for the tcgen05 engine (dist_tc.cu)
     DevBuf<float> p_l2;                    // DB
+    DevBuf<float> catch_thr;               // k x V catchword thresholds of the last catchword_thresholds call (catchwords.cu)
+    uint64_t catch_k = 0;
     DevBuf<float> lifted;                  // last lift_centers result (V x lifted_cols, column-major): input of lloyd_full
     uint64_t lifted_cols = 0;
 
@@ -355,6 +357,11 @@ void lift_centers(Ctx &c, uint64_t ncols, const float *in, uint64_t ld_in, float
 // ---- lloyd_full.cu (run_lloyds on the full-dimensional B)
 void lloyd_full(Ctx &c, uint64_t k, float *centers_inout, int max_reps, uint32_t *assign_out,
                 double *objective_out, int *iters_out);
+
+// ---- catchwords.cu (rth_highest_element per cluster, find_catchwords)
+void catchword_thresholds(Ctx &c, uint64_t k, uint64_t r, const uint32_t *cluster_of_doc_host, float *thresholds_out);
+void rth_highest_element(Ctx &c, uint64_t r, const uint64_t *docs_host, uint64_t ndocs, float *thresholds_out);
+void find_catchwords(Ctx &c, uint64_t k, const float *thresholds_host, double rho, int32_t *topic_of_word_out);
 
 // ---- dist_tc.cu (tcgen05 split-TF32 distance contraction)
 void split_tf32(Ctx &c, const float *x, size_t n, float *hi, float *lo);

@@ -28,10 +28,13 @@
 #include <cfloat>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace isle {
 
 namespace {
+
+using namespace tcptx;
 
 constexpr int BM = 128;            // documents per tile (UMMA M, cta_group::1)
 constexpr int BK = 32;             // tf32 elements per 128-byte swizzled row
@@ -41,20 +44,7 @@ constexpr int kThreads = 192;
 constexpr uint32_t kSmemBudget = 220 * 1024;
 
 // ---------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -74,14 +64,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     }
     __trap();
 }
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
@@ -93,30 +75,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO), the
-// leading-dimension offset is unused for swizzled K-major layouts (encoded 1), descriptor
-// version 1 (sm_100), layout type 2 = SWIZZLE_128B.  Units of 16 bytes.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
-{
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
 
 struct Params {
     const float *d2;        // ||P_d||^2
@@ -280,22 +239,6 @@ __global__ void split_tf32_kernel(const float *__restrict__ x, size_t n, float *
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        ISLE_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q));
-        ISLE_REQUIRE(sym && q == cudaDriverEntryPointSuccess, ISLE_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-        fn = reinterpret_cast<EncodeTiledFn>(sym);
-    }
-    return fn;
-}
 
 // rows x kp fp32 row-major, box = 32 k x box_rows, 128-byte swizzle, zero fill out of bounds
 CUtensorMap make_map(const float *base, uint64_t rows, uint64_t kp, uint32_t box_rows)

@@ -30,10 +30,13 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace isle {
 
 namespace {
+
+using namespace tcptx;
 
 constexpr uint32_t kGroups = 4;
 constexpr uint32_t kWarpMma = 4 * kGroups, kWarpTma = 4 * kGroups + 1;
@@ -46,19 +49,6 @@ constexpr uint32_t kBTile = 32 * 128;    // bytes: 32 rows (hi 16 | lo 16) x 32 
 constexpr uint32_t kStageBytes = kATile + kBTile;
 constexpr uint32_t kSpinLimit = 1u << 17;
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 __device__ __noinline__ void panel_timeout(uint32_t *diag, uint32_t code, uint32_t a, uint32_t b)
 {
@@ -117,14 +107,6 @@ __device__ __forceinline__ void mbar_wait2(uint64_t *bar_a, uint32_t parity_a, u
     }
     panel_timeout(diag, code + (pa ? 0x100u : 0u), da, db);
 }
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
 // D[tmem] (+)= A[tmem] * B[smem]; tf32 operands (fp32 bit patterns, low 13 mantissa bits ignored), fp32 accumulator
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
@@ -137,58 +119,8 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r)
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
-            taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-__device__ __forceinline__ uint32_t elect_one_sync()
-{
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 rx;\n\t"
-        ".reg .pred px;\n\t"
-        "elect.sync rx|px, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, px;\n\t"
-        "}"
-        : "=r"(pred));
-    return pred;
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
-{
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
 
-__device__ __forceinline__ uint32_t tf32_rna(float x)
-{
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    return h;
-}
 
 struct PanelParams {
     float *out;            // [nseg][m_total][16] partial results
@@ -386,22 +318,6 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        ISLE_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q));
-        ISLE_REQUIRE(sym && q == cudaDriverEntryPointSuccess, ISLE_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-        fn = reinterpret_cast<EncodeTiledFn>(sym);
-    }
-    return fn;
-}
 
 // fp32 [outer][inner] row-major (inner contiguous, row pitch `pitch` floats), box = box_inner x box_outer, zero fill out of bounds
 CUtensorMap make_map(const float *base, uint64_t inner, uint64_t outer, uint64_t pitch, uint32_t box_inner, uint32_t box_outer,

@@ -7,7 +7,7 @@
 // forwards to the C ABI in include/isle_cuda.h.  Explicit specialisations are ordinary (strong)
 // symbols, while the reference's `template class ISLE::FPSparseMatrix<float>;`
 // (src/sparseMatrix.cpp:2495-2510) emits weak ones, so the linker binds trainer.o to the
-// functions below and everything else (catchwords, topic model, output
+// functions below and everything else (topic model construction, output
 // writers) keeps running the reference's host code on the arrays this file fills.
 //
 //   reference member (include/sparseMatrix.h)            line   C ABI entry point
@@ -23,6 +23,8 @@
 //   FPSparseMatrix::left_multiply_by_U_Spectra            :309   isle_cuda_lift_centers
 //   FPSparseMatrix::cleanup_after_eigensolver             :260   isle_cuda_cleanup_eigensolver
 //   FPSparseMatrix::run_lloyds          :370   isle_cuda_lloyd_full
+//   SparseMatrix::rth_highest_element   :138   isle_cuda_rth_highest_element
+//   SparseMatrix::find_catchwords       :157   isle_cuda_find_catchwords
 //
 // Ownership follows the reference: every host array is new[]-allocated here to the size the
 // reference would have used and filled by the library; device memory belongs to the context.
@@ -32,6 +34,7 @@
 #include <cstdlib>
 #include <functional>
 #include <iostream>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -90,6 +93,36 @@ namespace ISLE
         int64_t new_nnzs = 0;
         check(isle_cuda_thresholds(ctx(), num_topics, zetas.data(), &new_nnzs), "thresholds");
         return (offset_t)new_nnzs;
+    }
+
+    // ---- stage G: catchword thresholds and catchwords ----------------------
+    // rth_highest_element is called once per topic from an OpenMP loop (src/trainer.cpp:587-589): the device
+    // context is single-caller, so the calls are serialised here; each one is a few kernels over the
+    // cluster's documents of the A matrix compute_thresholds() uploaded.
+    template<>
+    void SparseMatrix<float>::rth_highest_element(
+        const MKL_UINT r,
+        const std::vector<doc_id_t>& doc_partition,
+        float *thresholds)
+    {
+        static std::mutex m;
+        std::lock_guard<std::mutex> lock(m);
+        static_assert(sizeof(doc_id_t) == sizeof(uint64_t), "the C ABI assumes the reference's ILP64 index types");
+        check(isle_cuda_rth_highest_element(ctx(), (uint64_t)r, (const uint64_t *)doc_partition.data(),
+                                            (uint64_t)doc_partition.size(), thresholds), "rth_highest_element");
+    }
+
+    template<>
+    void SparseMatrix<float>::find_catchwords(
+        const doc_id_t num_topics,
+        const float *const thresholds,
+        std::vector<word_id_t> *catchwords)
+    {
+        std::vector<int32_t> topic_of_word(vocab_size());
+        check(isle_cuda_find_catchwords(ctx(), num_topics, thresholds, (double)rho_c, topic_of_word.data()), "find_catchwords");
+        for (word_id_t word = 0; word < vocab_size(); ++word)        // per topic in ascending word order, as :575-592
+            if (topic_of_word[word] >= 0)
+                catchwords[topic_of_word[word]].push_back(word);
     }
 
     // ---- stage B ----------------------------------------------------------------------------

@@ -36,6 +36,7 @@ BLOCK_KS_TOLERANCE = 1e-4
 KMEANS_INIT_REPS = 1
 MAX_KMEANS_LOWD_REPS = 10
 MAX_KMEANS_REPS = 10           # include/hyperparams.h:68
+RHO_C = 1.1                    # include/hyperparams.h:11
 
 
 class SparseMatrix:
@@ -85,6 +86,32 @@ class SparseMatrix:
         nn = C.c_int64()
         self.ctx.call("isle_cuda_thresholds", int(num_topics), ptr(zetas), C.byref(nn))
         return zetas, int(nn.value)
+
+
+    # -- catchword thresholds and catchwords (src/trainer.cpp:577-639)
+    def rth_highest_element(self, r: int, doc_partition) -> np.ndarray:
+        """src/sparseMatrix.cpp:491-524 for one cluster: returns thresholds float32[V]."""
+        docs = np.ascontiguousarray(doc_partition, dtype=np.uint64)
+        thr = np.zeros(self._vocab_size, dtype=np.float32)
+        self.ctx.call("isle_cuda_rth_highest_element", int(r), ptr(docs) if len(docs) else None, len(docs), ptr(thr))
+        return thr
+
+    def catchword_thresholds(self, num_topics: int, r: int, cluster_of_doc: np.ndarray, download: bool = True):
+        """All clusters in one device pass: ``cluster_of_doc`` is uint32[D] (0xFFFFFFFF = in no cluster).
+        Returns the (k, V) threshold matrix (topic-major, train()'s catchword_thresholds layout)."""
+        cl = np.ascontiguousarray(cluster_of_doc, dtype=np.uint32)
+        assert cl.shape[0] == self._num_docs
+        thr = np.zeros((int(num_topics), self._vocab_size), dtype=np.float32) if download else None
+        self.ctx.call("isle_cuda_catchword_thresholds", int(num_topics), int(r), ptr(cl), ptr(thr))
+        return thr
+
+    def find_catchwords(self, num_topics: int, thresholds: Optional[np.ndarray], rho: float = RHO_C) -> List[np.ndarray]:
+        """src/sparseMatrix.cpp:573-594.  ``thresholds`` (k, V) or None (the device copy of the last
+        catchword_thresholds).  Returns k ascending word-id arrays."""
+        thr = None if thresholds is None else np.ascontiguousarray(thresholds, dtype=np.float32)
+        tw = np.zeros(self._vocab_size, dtype=np.int32)
+        self.ctx.call("isle_cuda_find_catchwords", int(num_topics), ptr(thr), C.c_double(rho), ptr(tw))
+        return [np.nonzero(tw == t)[0] for t in range(int(num_topics))]
 
 
 class FPSparseMatrix:

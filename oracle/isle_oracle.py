@@ -489,6 +489,50 @@ def kmeans_objective_full(B_csc, C, a):
     return float((d2 - 2.0 * dots + c2[a.astype(np.int64)]).sum())
 
 
+# --------------------------------------------------------------------------- stage G
+def catchword_rank(num_docs: int, k: int) -> int:
+    """src/trainer.cpp:583: r = floor(eps2 * w0 * (float)num_docs / (float)(2 k)), eps2 = 1/3 and w0 = 1 as
+    doubles (include/hyperparams.h:8-10), the document count and 2k as floats."""
+    return int(math.floor((1.0 / 3.0) * 1.0 * float(F32(num_docs)) / float(F32(2.0 * k))))
+
+
+def rth_highest_element(vals, rows, offsets, V: int, docs, r: int):
+    """src/sparseMatrix.cpp:491-524: per word the r-th highest normalised value among the documents of one
+    cluster when the word occurs in MORE than r of them; otherwise 0 -- except when r >= cluster size and the
+    word occurs in every document of the cluster, then the smallest value."""
+    thr = np.zeros(V, dtype=F32)
+    docs = np.asarray(docs, dtype=np.int64)
+    if len(docs) == 0:
+        return thr
+    lens = (offsets[docs + 1] - offsets[docs]).astype(np.int64)
+    idx = np.repeat(offsets[docs], lens) + (np.arange(lens.sum()) - np.repeat(np.cumsum(lens) - lens, lens))
+    w, v = rows[idx].astype(np.int64), vals[idx].astype(F32)
+    order = np.lexsort((-v.astype(np.float64), w))          # by word, value descending
+    w, v = w[order], v[order]
+    cnt = np.bincount(w, minlength=V)
+    start = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    big = cnt > r
+    thr[big] = v[start[big] + r - 1]
+    if r >= len(docs):
+        full = (~big) & (cnt == len(docs))
+        thr[full] = v[start[full] + cnt[full] - 1]
+    return thr
+
+
+def find_catchwords(thr, rho=1.1):
+    """src/sparseMatrix.cpp:573-594: word w is a catchword of topic t iff thr[t, w] > rho * thr[o, w] for every
+    other topic o (fp32 compare of thr against the fp64 product, as the reference's expression evaluates).
+    thr is (k, V).  Returns a list of k ascending word arrays."""
+    k, V = thr.shape
+    t64 = thr.astype(np.float64)
+    out = []
+    for t in range(k):
+        others = np.delete(t64, t, axis=0)
+        ok = np.all(t64[t][None, :] > rho * others, axis=0) if k > 1 else np.zeros(V, bool)
+        out.append(np.nonzero(ok)[0].astype(np.int64))
+    return out
+
+
 # --------------------------------------------------------------------------- comparisons
 def principal_angle_sin(U1, U2):
     """sin of the largest principal angle between span(U1) and span(U2) (orthonormal cols)."""

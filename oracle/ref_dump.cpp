@@ -15,13 +15,14 @@
  *   stage D  kmeans_init_on_projected_space     (:529-530)
  *   stage E  run_lloyds_on_projected_space + left_multiply_by_U_Spectra (:546-550)
  *   stage F  run_lloyds on the full-dimensional B   (:559-571)
+ *   stage G  rth_highest_element per cluster + find_catchwords   (:573-639)
  *
  * Input : <corpus.bin>  = int64 V, D, nnz ; int64 offsets[D+1] ; uint32 rows[nnz] ;
  *                         uint32 counts[nnz]      (doc-major CSC of raw counts)
  * Output: <outdir>/<name>.bin raw little-endian arrays + meta.json with sizes and
  *         per-stage wall-clock seconds (used as the CPU baseline by bench.py).
  *
- * usage: ref_dump <corpus.bin> <outdir> <k> [--upto A|B|C|D|E|F] [--mask mask.u8]
+ * usage: ref_dump <corpus.bin> <outdir> <k> [--upto A|B|C|D|E|F|G] [--mask mask.u8]
  *                 [--centers centers_lowd.f32]   (override k-means++ seeds for Lloyd)
  *                 [--lloyd-iters n] [--srand seed]
  */
@@ -34,6 +35,7 @@
 #include <vector>
 
 #include "sparseMatrix.h"
+#include "hyperparams.h"
 
 using namespace ISLE;
 
@@ -92,7 +94,7 @@ int main(int argc, char **argv)
     }
     const std::string corpus = argv[1], out = argv[2];
     const doc_id_t k = (doc_id_t)std::atol(argv[3]);
-    char upto = 'F';
+    char upto = 'G';
     std::string mask_file, centers_file;
     int lloyd_iters = MAX_KMEANS_LOWD_REPS;
     for (int i = 4; i < argc; ++i) {
@@ -258,8 +260,35 @@ int main(int argc, char **argv)
         dump(out, "full_assign", assign.data(), assign.size());
         dump(out, "full_centers", centers.data(), centers.size());
     }
+    std::fprintf(meta, ", \"t_lloyd_full\": %.6f", t_lf);
+    if (upto == 'F') { delete[] closest_full; std::fprintf(meta, "}\n"); std::fclose(meta); return 0; }
+
+    /* ---- stage G: catchword thresholds and catchwords (trainer.cpp:573-639) ---- */
+    t0 = now_s();
+    for (doc_id_t topic = 0; topic != k; ++topic)                       /* :573-575 */
+        for (auto d = closest_full[topic].begin(); d < closest_full[topic].end(); ++d)
+            *d = original_cols[*d];
+    const MKL_UINT r = (MKL_UINT)std::floor(eps2_c * w0_c * (FPTYPE)D / (FPTYPE)(2.0 * k));   /* :583 */
+    std::vector<A_TYPE> cthr((size_t)k * (size_t)V);
+    for (doc_id_t topic = 0; topic < k; ++topic)                         /* :587-589 (pfor in the reference) */
+        A_sp->rth_highest_element(r, closest_full[topic], cthr.data() + (size_t)topic * (size_t)V);
+    auto catchwords = new std::vector<word_id_t>[k];
+    A_sp->find_catchwords(k, cthr.data(), catchwords);                   /* :635 */
+    double t_cw = now_s() - t0;
+    {
+        std::vector<uint32_t> cl((size_t)D, 0xffffffffu);               /* cluster of every ORIGINAL document */
+        for (doc_id_t c = 0; c < k; ++c)
+            for (auto d : closest_full[c]) cl[d] = (uint32_t)c;
+        dump(out, "catch_cluster_of_doc", cl.data(), cl.size());
+        dump(out, "catch_thresholds", cthr.data(), cthr.size());
+        std::vector<uint32_t> pairs;
+        for (doc_id_t c = 0; c < k; ++c)
+            for (auto w : catchwords[c]) { pairs.push_back((uint32_t)c); pairs.push_back((uint32_t)w); }
+        dump(out, "catchwords", pairs.data(), pairs.size());
+    }
+    delete[] catchwords;
     delete[] closest_full;
-    std::fprintf(meta, ", \"t_lloyd_full\": %.6f}\n", t_lf);
+    std::fprintf(meta, ", \"catch_r\": %llu, \"t_catchwords\": %.6f}\n", (unsigned long long)r, t_cw);
     std::fclose(meta);
     delete B;
     delete A_sp;

@@ -40,6 +40,16 @@ def golden_c1_stageF():
 
 
 @pytest.fixture(scope="session")
+def golden_tiny_stageG():
+    return dict(np.load(os.path.join(GOLDEN, "tiny_stageG.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_c1_stageG():
+    return dict(np.load(os.path.join(GOLDEN, "c1_stageG.npz")))
+
+
+@pytest.fixture(scope="session")
 def corpus_c1():
     from isle_b200 import corpus
     return corpus.generate("c1")

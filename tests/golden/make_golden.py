@@ -68,14 +68,33 @@ def stage_f(name):
                 assign=ld("full_assign", np.uint32))
 
 
+def stage_g(name):
+    """Stage G (rth_highest_element per cluster + find_catchwords): the partition of the ORIGINAL
+    documents that went in, the rank r, the k x V threshold matrix and the (topic, word) catchword pairs that came out."""
+    c, tmp, out, ld = run(name)
+    meta = json.load(open(os.path.join(tmp, "meta.json")))
+    return dict(corpus_sha=out["corpus_sha"], A_vals_sha=out["A_vals_sha"], r=meta["catch_r"],
+                cluster_of_doc=ld("catch_cluster_of_doc", np.uint32), thresholds=ld("catch_thresholds", np.float32),
+                catchwords=ld("catchwords", np.uint32).reshape(-1, 2))
+
+
 def main_stage_f():
     here = os.path.dirname(__file__)
     for name in ("tiny", "c1"):
         np.savez_compressed(os.path.join(here, f"{name}_stageF.npz"), **stage_f(name))
 
+
+def main_stage_g():
+    here = os.path.dirname(__file__)
+    for name in ("tiny", "c1"):
+        np.savez_compressed(os.path.join(here, f"{name}_stageG.npz"), **stage_g(name))
+
 if __name__ == "__main__":
     if "--stage-f" in sys.argv:      # adds the stage-F fixtures without touching the stage A-E ones
         main_stage_f()
+        sys.exit(0)
+    if "--stage-g" in sys.argv:
+        main_stage_g()
         sys.exit(0)
     here = os.path.dirname(__file__)
     c, tmp, out, ld = run("tiny")
@@ -102,3 +121,4 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(here, "c1.npz"), **out)
 
     main_stage_f()
+    main_stage_g()

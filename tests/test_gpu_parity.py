@@ -436,6 +436,58 @@ def test_lloyd_full_from_device_resident_lifted_centers(ctx, golden_tiny):
     assert abs(dev["objective"] - B.last_lloyd_full["objective"]) <= 1e-12 * dev["objective"]   # fp64 atomics: order varies
 
 
+# ---------------------------------------------------------------- stage G: catchword thresholds, catchwords
+def _upload_A(ctx, c):
+    from isle_b200.sparse_matrix import SparseMatrix
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    A = SparseMatrix(c.V, c.D, ctx)
+    A.populate_normalized(vals, c.rows, c.offsets, avg, nz)
+    return A, vals
+
+
+@pytest.mark.parametrize("name", ["tiny", "c1"])
+def test_catchwords_match_reference(ctx, name, golden_tiny_stageG, golden_c1_stageG, corpus_c1):
+    """SURVEY 8(f) row 2 through the C ABI, both calling conventions, bit-exact against the reference's own
+    thresholds and catchwords for the same partition."""
+    from isle_b200 import corpus
+    g = golden_tiny_stageG if name == "tiny" else golden_c1_stageG
+    c = corpus.generate("tiny") if name == "tiny" else corpus_c1
+    A, vals = _upload_A(ctx, c)
+    r, cl = int(g["r"]), g["cluster_of_doc"]
+    thr_ref = g["thresholds"].reshape(c.k, c.V)
+    thr = A.catchword_thresholds(c.k, r, cl)                      # all clusters in one pass
+    assert np.array_equal(thr.view(np.uint32), thr_ref.view(np.uint32))
+    for t in (0, c.k // 2, c.k - 1):                              # the reference's per-topic convention
+        one = A.rth_highest_element(r, np.nonzero(cl == t)[0])
+        assert np.array_equal(one.view(np.uint32), thr_ref[t].view(np.uint32))
+    for source in (thr, None):                                    # host matrix, then the device-resident copy
+        cw = A.find_catchwords(c.k, source)
+        pairs = np.array([(t, w) for t in range(c.k) for w in cw[t]], dtype=np.uint32).reshape(-1, 2)
+        assert np.array_equal(pairs, g["catchwords"])
+
+
+def test_rth_highest_element_edges(ctx):
+    """Branches of src/sparseMatrix.cpp:496-520 against the oracle: empty cluster, count == r, r >= cluster size,
+    documents outside every cluster, a cluster id with no documents."""
+    from isle_b200 import corpus
+    c = corpus.generate("tiny")
+    A, vals = _upload_A(ctx, c)
+    rng = np.random.default_rng(9)
+    assert np.all(A.rth_highest_element(3, []) == 0)
+    for docs, r in ((rng.choice(c.D, 40, replace=False), 5), (np.arange(3), 3), (np.arange(7), 50), (np.array([11]), 1)):
+        ref = O.rth_highest_element(vals, c.rows, c.offsets, c.V, np.sort(docs), r)
+        assert np.array_equal(A.rth_highest_element(r, np.sort(docs)).view(np.uint32), ref.view(np.uint32))
+    cl = rng.integers(0, 6, c.D).astype(np.uint32)
+    cl[cl == 5] = 0xFFFFFFFF                                      # in no cluster
+    cl[cl == 4] = 0                                               # cluster 4 stays empty
+    thr = A.catchword_thresholds(5, 20, cl)
+    ref = np.stack([O.rth_highest_element(vals, c.rows, c.offsets, c.V, np.nonzero(cl == t)[0], 20) for t in range(5)])
+    assert np.array_equal(thr.view(np.uint32), ref.view(np.uint32)) and np.all(thr[4] == 0)
+    cw, cw_ref = A.find_catchwords(5, thr), O.find_catchwords(ref)
+    assert all(np.array_equal(a, b) for a, b in zip(cw, cw_ref))
+    assert all(len(x) == 0 for x in A.find_catchwords(1, thr[:1]))   # k = 1: the reference's loop never sets the flag
+
+
 # ---------------------------------------------------------------- end to end
 def test_spectral_core_end_to_end_c1(ctx, golden_c1, corpus_c1):
     """Stages A-E through the public call; k-means is checked through rotation-invariant

@@ -208,6 +208,37 @@ def test_lloyd_full_matches_reference(name, golden_tiny_stageF, golden_c1_stageF
     assert 1 <= iters <= 10
 
 
+@pytest.mark.parametrize("name", ["tiny", "c1"])
+def test_catchwords_match_reference(name, golden_tiny_stageG, golden_c1_stageG, corpus_c1):
+    """rth_highest_element per cluster + find_catchwords restated, bit-exact against the
+    reference's own output (tests/golden/*_stageG.npz, made by ref_dump stage G)."""
+    from isle_b200 import corpus
+    g = golden_tiny_stageG if name == "tiny" else golden_c1_stageG
+    c = corpus.generate("tiny") if name == "tiny" else corpus_c1
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    r = int(g["r"])
+    assert r == O.catchword_rank(c.D, c.k)
+    cl = g["cluster_of_doc"]
+    thr = np.stack([O.rth_highest_element(vals, c.rows, c.offsets, c.V, np.nonzero(cl == t)[0], r) for t in range(c.k)])
+    assert np.array_equal(thr.view(np.uint32), g["thresholds"].reshape(c.k, c.V).view(np.uint32))
+    cw = O.find_catchwords(thr)
+    pairs = np.array([(t, w) for t in range(c.k) for w in cw[t]], dtype=np.uint32).reshape(-1, 2)
+    assert np.array_equal(pairs, g["catchwords"])
+
+
+def test_rth_highest_element_edges():
+    """Branches of src/sparseMatrix.cpp:496-520: empty cluster, count == r (not > r), r >= cluster size."""
+    offsets = np.array([0, 2, 4, 5], dtype=np.int64)
+    rows = np.array([0, 1, 0, 1, 0], dtype=np.uint32)
+    vals = np.array([3.0, 1.0, 2.0, 5.0, 4.0], dtype=np.float32)
+    assert np.all(O.rth_highest_element(vals, rows, offsets, 3, [], 1) == 0)
+    assert np.array_equal(O.rth_highest_element(vals, rows, offsets, 3, [0, 1, 2], 1), [4.0, 5.0, 0.0])   # counts 3, 2 > r = 1
+    assert np.array_equal(O.rth_highest_element(vals, rows, offsets, 3, [0, 1, 2], 2), [3.0, 0.0, 0.0])   # word 1: count 2 == r
+    # r >= cluster size: the smallest value, only for words present in every document of the cluster
+    assert np.array_equal(O.rth_highest_element(vals, rows, offsets, 3, [0, 1], 2), [2.0, 1.0, 0.0])
+    assert np.array_equal(O.rth_highest_element(vals, rows, offsets, 3, [0, 1, 2], 3), [2.0, 0.0, 0.0])
+
+
 def test_kmeanspp_invariants(golden_tiny):
     g = golden_tiny
     V, k = int(g["V"]), int(g["k"])
