@@ -340,10 +340,39 @@ def bench_ours(args):
     ctx.call("isle_cuda_reset_stats")
     fobj, fit, fms = C.c_double(), C.c_int(), C.c_double()
     ctx.call("isle_cuda_timer_start")
-    ctx.call("isle_cuda_lloyd_full", k, None, 10, None, C.byref(fobj), C.byref(fit))
+    f_assign = np.zeros(max(state["DB"], 1), np.uint32)
+    ctx.call("isle_cuda_lloyd_full", k, None, 10, ptr(f_assign), C.byref(fobj), C.byref(fit))
     ctx.call("isle_cuda_timer_stop", C.byref(fms))
     stf = {n: ctx.stat(n) for n in ("lloyd_full_iter_ms", "lloyd_full_assign_ms", "lloyd_full_update_ms",
                                     "lloyd_full_assign_flops")}
+    # ---- SURVEY 8(f) row 2, first half: catchword thresholds of all clusters + catchwords (trainer.cpp:577-639), from the
+    # partition stage F just produced; single-GPU contexts only for now
+    cw = None
+    if world == 1:
+        oc = np.zeros(max(state["DB"], 1), np.uint64)
+        ctx.call("isle_cuda_download_B", None, None, None, ptr(oc))
+        cl = np.full(D, 0xFFFFFFFF, np.uint32)
+        cl[oc[:state["DB"]].astype(np.int64)] = f_assign[:state["DB"]]
+        r_catch = int(np.floor((1.0 / 3.0) * 1.0 * float(np.float32(D)) / float(np.float32(2.0 * k))))   # trainer.cpp:583
+        tw = np.zeros(V, np.int32)
+        cms = C.c_double()
+        ctx.call("isle_cuda_timer_start")
+        ctx.call("isle_cuda_catchword_thresholds", k, r_catch, ptr(cl), None)
+        ctx.call("isle_cuda_find_catchwords", k, None, C.c_double(1.1), ptr(tw))
+        ctx.call("isle_cuda_timer_stop", C.byref(cms))
+        cw = {"what": "SURVEY 8(f) row 2 first half: rth_highest_element for all clusters + find_catchwords, device-resident A, "
+                      "not part of the metric", "ms": cms.value, "r": r_catch, "catchwords": int((tw >= 0).sum()),
+              "candidate_segments": int(ctx.stat("cw_candidates")),
+              "count_ms": ctx.stat("cw_count_ms"), "scatter_ms": ctx.stat("cw_scatter_ms"), "sort_ms": ctx.stat("cw_sort_ms"),
+              "algorithmic_GBps": (2.0 * nnz * 8.0 + 2.0 * k * V * 4.0) / (cms.value * 1e-3) / 1e9 if cms.value > 0 else None}
+        # ---- SURVEY 8(f) row 2, second half: construct_topic_model from those catchwords and that partition
+        rank_tm = int(np.uint64(5.0 * 1.0 * float(np.float32(D)) / (float(np.float32(k)) * 2.0)))      # sparseMatrix.cpp:716
+        n_tm, tms = C.c_uint64(), C.c_double()
+        ctx.call("isle_cuda_timer_start")
+        ctx.call("isle_cuda_construct_topic_model", k, ptr(tw), ptr(cl), rank_tm, None, C.byref(n_tm))
+        ctx.call("isle_cuda_timer_stop", C.byref(tms))
+        cw["topic_model"] = {"what": "construct_topic_model (sparseMatrix.cpp:597-838), model left on the device", "ms": tms.value,
+                             "doc_topic_sums": int(n_tm.value), "rank_threshold": rank_tm}
     ctx.call("isle_cuda_set_profiling", 0)
 
     # ---- (2) end to end: host buffers in, host results out, every step
@@ -408,7 +437,8 @@ def bench_ours(args):
                                          "objective": fobj.value, "assign_ms": stf["lloyd_full_assign_ms"],
                                          "update_ms": stf["lloyd_full_update_ms"],
                                          "assign_gather_tflops": (stf["lloyd_full_assign_flops"] / (stf["lloyd_full_assign_ms"] * 1e-3) / 1e12
-                                                                  if stf["lloyd_full_assign_ms"] > 0 else None)}},
+                                                                  if stf["lloyd_full_assign_ms"] > 0 else None)},
+                          "catchwords": cw},
             "alloc": {"driver_allocs_in_timed_region": st["alloc_misses"], "cache_hits_per_step": st["alloc_hits"] / args.steps},
         }
         if not args.no_cpu_baseline and world == 1:

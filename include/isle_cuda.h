@@ -157,6 +157,19 @@ int isle_cuda_catchword_thresholds(isle_cuda_ctx *ctx, uint64_t k, uint64_t r, c
  * thresholds: k x V host matrix, or NULL = the device matrix of the last isle_cuda_catchword_thresholds. */
 int isle_cuda_find_catchwords(isle_cuda_ctx *ctx, uint64_t k, const float *thresholds, double rho,
                               int32_t *topic_of_word_out);
+/* SURVEY 8(f) row 2, second half.  Replaces SparseMatrix::construct_topic_model (src/sparseMatrix.cpp:597-838,
+ * called at src/trainer.cpp:645-651).  topic_of_word[w] = the topic w is a catchword of, or -1 (what
+ * isle_cuda_find_catchwords returns); cluster_of_doc[d] = cluster of original document d or 0xFFFFFFFF (closest_docs);
+ * rank_threshold = (uint)(eps3 w0 (float)D / ((float)k 2.0)) as the reference computes it (:716).
+ * model_out (V x k column-major, may be NULL): column t = l1-normalised sum of the documents whose catchword mass for t
+ * exceeds the topic's threshold plus the documents of cluster t; a topic nobody contributes to divides by zero exactly
+ * as the reference's FPscal(1/asum) does.  *num_entries_out = number of non-zero (document, topic) catchword sums,
+ * which isle_cuda_doc_topic_sums then copies out in (document, topic) order (the reference's doc_topic_sum list after
+ * its final sort, :789-793; sums are bit-identical to the reference's, the model agrees to fp32 rounding). */
+int isle_cuda_construct_topic_model(isle_cuda_ctx *ctx, uint64_t k, const int32_t *topic_of_word,
+                                    const uint32_t *cluster_of_doc, uint64_t rank_threshold, float *model_out,
+                                    uint64_t *num_entries_out);
+int isle_cuda_doc_topic_sums(isle_cuda_ctx *ctx, uint32_t *docs, uint32_t *topics, float *sums);
 /* Harness only (no reference counterpart): one block Gram-Schmidt pass of BlockKs::expand
  * (block-ks/restarted_block_ks.h:83-84) on caller data, C = W^T F then F -= W C, with a chosen engine
  * (0 = fp32 FMA, 1 = fp32 FMA with vector loads, 2 = tcgen05 split TF32), so the panel engines of the

@@ -69,6 +69,8 @@ SIGNATURES = {
     "isle_cuda_rth_highest_element": [_vp, _u64, _vp, _u64, _vp],
     "isle_cuda_catchword_thresholds": [_vp, _u64, _u64, _vp, _vp],
     "isle_cuda_find_catchwords": [_vp, _u64, _vp, C.c_double, _vp],
+    "isle_cuda_construct_topic_model": [_vp, _u64, _vp, _vp, _u64, _vp, C.POINTER(C.c_uint64)],
+    "isle_cuda_doc_topic_sums": [_vp, _vp, _vp, _vp],
     "isle_cuda_panel_products": [_vp, C.c_int64, _int, _int, _vp, _vp, _vp, _int],
     "isle_cuda_lloyd_full": [_vp, _u64, _vp, _int, _vp, C.POINTER(C.c_double), C.POINTER(_int)],
     "isle_cuda_cleanup_eigensolver": [_vp],

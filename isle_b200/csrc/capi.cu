@@ -285,6 +285,17 @@ int isle_cuda_find_catchwords(isle_cuda_ctx *h, uint64_t k, const float *thresho
     return guarded(h, [&](Ctx &c) { find_catchwords(c, k, thresholds, rho, topic_of_word_out); });
 }
 
+int isle_cuda_construct_topic_model(isle_cuda_ctx *h, uint64_t k, const int32_t *topic_of_word, const uint32_t *cluster_of_doc,
+                                    uint64_t rank_threshold, float *model_out, uint64_t *num_entries_out)
+{
+    return guarded(h, [&](Ctx &c) { construct_topic_model(c, k, topic_of_word, cluster_of_doc, rank_threshold, model_out, num_entries_out); });
+}
+
+int isle_cuda_doc_topic_sums(isle_cuda_ctx *h, uint32_t *docs, uint32_t *topics, float *sums)
+{
+    return guarded(h, [&](Ctx &c) { download_doc_topic_sums(c, docs, topics, sums); });
+}
+
 int isle_cuda_panel_products(isle_cuda_ctx *h, int64_t n, int rows, int b, const float *W, float *F_inout, float *C_out, int engine)
 {
     return guarded(h, [&](Ctx &c) { panel_products(c, n, rows, b, W, F_inout, C_out, engine); });

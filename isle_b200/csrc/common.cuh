@@ -247,6 +247,9 @@ struct Ctx {
     DevBuf<float> p_l2;                    // DB
     DevBuf<float> catch_thr;               // k x V catchword thresholds of the last catchword_thresholds call (catchwords.cu)
     uint64_t catch_k = 0;
+    DevBuf<uint32_t> tm_doc, tm_topic;     // (document, topic, sum) list of the last construct_topic_model (topic_model.cu)
+    DevBuf<float> tm_val, tm_model;        // ... its sums; the V x k model (column-major)
+    int64_t tm_entries = 0;
     DevBuf<float> lifted;                  // last lift_centers result (V x lifted_cols, column-major): input of lloyd_full
     uint64_t lifted_cols = 0;
 
@@ -362,6 +365,11 @@ void lloyd_full(Ctx &c, uint64_t k, float *centers_inout, int max_reps, uint32_t
 void catchword_thresholds(Ctx &c, uint64_t k, uint64_t r, const uint32_t *cluster_of_doc_host, float *thresholds_out);
 void rth_highest_element(Ctx &c, uint64_t r, const uint64_t *docs_host, uint64_t ndocs, float *thresholds_out);
 void find_catchwords(Ctx &c, uint64_t k, const float *thresholds_host, double rho, int32_t *topic_of_word_out);
+
+// ---- topic_model.cu (construct_topic_model)
+void construct_topic_model(Ctx &c, uint64_t k, const int32_t *topic_of_word_host, const uint32_t *cluster_of_doc_host,
+                           uint64_t rank_threshold, float *model_out, uint64_t *num_entries_out);
+void download_doc_topic_sums(Ctx &c, uint32_t *docs, uint32_t *topics, float *sums);
 
 // ---- dist_tc.cu (tcgen05 split-TF32 distance contraction)
 void split_tf32(Ctx &c, const float *x, size_t n, float *hi, float *lo);

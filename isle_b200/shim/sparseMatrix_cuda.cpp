@@ -7,7 +7,7 @@
 // forwards to the C ABI in include/isle_cuda.h.  Explicit specialisations are ordinary (strong)
 // symbols, while the reference's `template class ISLE::FPSparseMatrix<float>;`
 // (src/sparseMatrix.cpp:2495-2510) emits weak ones, so the linker binds trainer.o to the
-// functions below and everything else (topic model construction, output
+// functions below and everything else (loaders, metrics, output
 // writers) keeps running the reference's host code on the arrays this file fills.
 //
 //   reference member (include/sparseMatrix.h)            line   C ABI entry point
@@ -25,6 +25,7 @@
 //   FPSparseMatrix::run_lloyds          :370   isle_cuda_lloyd_full
 //   SparseMatrix::rth_highest_element   :138   isle_cuda_rth_highest_element
 //   SparseMatrix::find_catchwords       :157   isle_cuda_find_catchwords
+//   SparseMatrix::construct_topic_model (8f row 2)        :162   isle_cuda_construct_topic_model + isle_cuda_doc_topic_sums
 //
 // Ownership follows the reference: every host array is new[]-allocated here to the size the
 // reference would have used and filled by the library; device memory belongs to the context.
@@ -36,6 +37,7 @@
 #include <iostream>
 #include <mutex>
 #include <stdexcept>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -123,6 +125,63 @@ namespace ISLE
         for (word_id_t word = 0; word < vocab_size(); ++word)        // per topic in ascending word order, as :575-592
             if (topic_of_word[word] >= 0)
                 catchwords[topic_of_word[word]].push_back(word);
+    }
+
+    // ---- stage H: topic model ---------------------------------------------------
+    // construct_topic_model (src/sparseMatrix.cpp:597-838), called at src/trainer.cpp:645-651.  The device builds
+    // the (document, topic) catchword sums, the per-topic thresholds and the model; this function fills the three
+    // host lists the trainer's writers read (catchword_topics, doc_topic_sum, top_topic_pairs) from what comes back.
+    template<>
+    void SparseMatrix<float>::construct_topic_model(
+        DenseMatrix<FPTYPE>& Model,
+        const doc_id_t num_topics,
+        const std::vector<doc_id_t> *const closest_docs,
+        const std::vector<word_id_t> *const catchwords,
+        bool,
+        std::vector<std::tuple<int, int, doc_id_t> >* top_topic_pairs,
+        std::vector<std::pair<word_id_t, int> >* catchword_topics,
+        std::vector<std::tuple<doc_id_t, doc_id_t, FPTYPE> >*  doc_topic_sum)
+    {
+        assert(Model.vocab_size() == vocab_size());
+        assert(Model.num_docs() == num_topics);
+        std::vector<int32_t> topic_of_word(vocab_size(), -1);
+        for (doc_id_t topic = 0; topic < num_topics; ++topic)
+            for (auto w : catchwords[topic]) topic_of_word[w] = (int32_t)topic;
+        std::vector<uint32_t> cluster_of_doc(num_docs(), 0xFFFFFFFFu);
+        for (doc_id_t topic = 0; topic < num_topics; ++topic)
+            for (auto d : closest_docs[topic]) cluster_of_doc[d] = (uint32_t)topic;
+        const uint64_t rank_threshold = (doc_id_t)(eps3_c*w0_c*(FPTYPE)num_docs() / ((FPTYPE)num_topics * 2.0));   // :716
+        assert(rank_threshold > 0);
+        uint64_t n = 0;
+        check(isle_cuda_construct_topic_model(ctx(), num_topics, topic_of_word.data(), cluster_of_doc.data(), rank_threshold,
+                                              Model.data(), &n), "construct_topic_model");
+        if (catchword_topics != NULL)                                   // sorted by word (:619-621)
+            for (word_id_t w = 0; w < vocab_size(); ++w)
+                if (topic_of_word[w] >= 0) catchword_topics->push_back(std::make_pair(w, (int)topic_of_word[w]));
+        if (doc_topic_sum == NULL && top_topic_pairs == NULL) return;
+        std::vector<uint32_t> docs(n), topics(n);
+        std::vector<float> sums(n);
+        check(isle_cuda_doc_topic_sums(ctx(), docs.data(), topics.data(), sums.data()), "doc_topic_sums");
+        if (top_topic_pairs != NULL) {                                  // :683-703: strict >, entries in topic order
+            uint64_t i = 0;
+            while (i < n) {
+                const uint32_t doc = docs[i];
+                float max = 0.0f, max2 = 0.0f;
+                int max_topic = -1, max2_topic = -1;
+                for (; i < n && docs[i] == doc; ++i) {
+                    if (sums[i] > max) { max2 = max; max2_topic = max_topic; max = sums[i]; max_topic = (int)topics[i]; }
+                    else if (sums[i] > max2) { max2 = sums[i]; max2_topic = (int)topics[i]; }
+                }
+                if (max_topic >= 0 && max2_topic >= 0)
+                    top_topic_pairs->push_back(std::make_tuple(max_topic, max2_topic, (doc_id_t)doc));
+            }
+        }
+        if (doc_topic_sum != NULL) {                                    // final order of the reference: (doc, topic) (:789-793)
+            doc_topic_sum->reserve(n);
+            for (uint64_t i = 0; i < n; ++i)
+                doc_topic_sum->emplace_back((doc_id_t)docs[i], (doc_id_t)topics[i], sums[i]);
+        }
+        std::cout << "Size of doc_topic_sum array: " << n << std::endl;
     }
 
     // ---- stage B ----------------------------------------------------------------------------

@@ -37,6 +37,7 @@ KMEANS_INIT_REPS = 1
 MAX_KMEANS_LOWD_REPS = 10
 MAX_KMEANS_REPS = 10           # include/hyperparams.h:68
 RHO_C = 1.1                    # include/hyperparams.h:11
+W0_C, EPS3_C = 1.0, 5.0        # include/hyperparams.h:8,12
 
 
 class SparseMatrix:
@@ -112,6 +113,43 @@ class SparseMatrix:
         tw = np.zeros(self._vocab_size, dtype=np.int32)
         self.ctx.call("isle_cuda_find_catchwords", int(num_topics), ptr(thr), C.c_double(rho), ptr(tw))
         return [np.nonzero(tw == t)[0] for t in range(int(num_topics))]
+
+
+    def construct_topic_model(self, num_topics: int, cluster_of_doc: np.ndarray, catchwords, want_pairs: bool = True):
+        """src/sparseMatrix.cpp:597-838.  ``cluster_of_doc`` uint32[D] (closest_docs as a map, 0xFFFFFFFF = none),
+        ``catchwords`` a list of k word-id arrays.  Returns (Model float32[V, k], (doc, topic, sum) arrays in
+        (doc, topic) order, top_topic_pairs int64[n, 3] in document order or None)."""
+        k = int(num_topics)
+        tw = np.full(self._vocab_size, -1, dtype=np.int32)
+        for t in range(k):
+            tw[np.asarray(catchwords[t], dtype=np.int64)] = t
+        cl = np.ascontiguousarray(cluster_of_doc, dtype=np.uint32)
+        assert cl.shape[0] == self._num_docs
+        # (doc_id_t)(eps3_c * w0_c * (FPTYPE)num_docs() / ((FPTYPE)num_topics * 2.0))   (:716)
+        rank = int(np.uint64(EPS3_C * W0_C * float(np.float32(self._num_docs)) / (float(np.float32(k)) * 2.0)))
+        model = np.zeros((k, self._vocab_size), dtype=np.float32)
+        n = C.c_uint64()
+        self.ctx.call("isle_cuda_construct_topic_model", k, ptr(tw), ptr(cl), rank, ptr(model), C.byref(n))
+        n = int(n.value)
+        docs, topics, sums = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.float32)
+        self.ctx.call("isle_cuda_doc_topic_sums", ptr(docs), ptr(topics), ptr(sums))
+        pairs = None
+        if want_pairs:                                       # :683-703, strict > in topic order
+            out = []
+            bounds = np.searchsorted(docs, np.arange(self._num_docs + 1))
+            for d in range(self._num_docs):
+                mx = mx2 = np.float32(0.0)
+                t1 = t2 = -1
+                for i in range(bounds[d], bounds[d + 1]):
+                    x = sums[i]
+                    if x > mx:
+                        mx2, t2, mx, t1 = mx, t1, x, int(topics[i])
+                    elif x > mx2:
+                        mx2, t2 = x, int(topics[i])
+                if t1 >= 0 and t2 >= 0:
+                    out.append((t1, t2, d))
+            pairs = np.array(out, dtype=np.int64).reshape(-1, 3)
+        return model.T.copy(), (docs, topics, sums), pairs
 
 
 class FPSparseMatrix:

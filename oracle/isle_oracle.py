@@ -533,6 +533,90 @@ def find_catchwords(thr, rho=1.1):
     return out
 
 
+def construct_topic_model(vals, rows, offsets, V: int, k: int, cluster_of_doc, catchwords, eps3=5.0, w0=1.0):
+    """src/sparseMatrix.cpp:597-838 construct_topic_model.  ``cluster_of_doc`` uint32[D] (0xFFFFFFFF = none) is the
+    closest_docs partition of the original documents, ``catchwords`` a list of k word arrays.  Returns
+    (Model float32[V, k] column-stochastic, dts = (doc, topic, sum) arrays in (doc, topic) order, top_topic_pairs
+    int array [n, 3] in document order).
+
+    * doc_topic_sum[doc][topic] = fp32 sum, in position order, of the document's values on topic's catchwords (:652-668);
+      non-zero entries are listed by (doc, topic) (:669-678)
+    * top two topics per doc by strict > in topic order (:683-703)
+    * model_threshold[topic] = rank_threshold-th largest sum of the topic (0 when fewer entries or no catchwords), with
+      rank_threshold = (uint)(eps3 w0 (float)D / ((float)k 2.0)) (:716-751)
+    * Model[:, topic] += every document whose sum for the topic exceeds the threshold, plus -- for EVERY document of a
+      cluster, the variable is misnamed doc_in_catchless_topic -- the document's own cluster (:787-817); columns are then
+      scaled to unit l1 norm (:822-826).  The reference accumulates in fp32 in document order; this restatement does the
+      same per column through np.add.at on float32 (same order of additions)."""
+    D = len(offsets) - 1
+    topic_of_word = np.full(V, -1, dtype=np.int64)
+    for t in range(k):
+        topic_of_word[np.asarray(catchwords[t], dtype=np.int64)] = t
+    lens = np.diff(offsets).astype(np.int64)
+    doc_of = np.repeat(np.arange(D, dtype=np.int64), lens)
+    tw = topic_of_word[rows.astype(np.int64)]
+    sel = tw >= 0
+    # fp32 sequential sums per (doc, topic) in position order
+    key = doc_of[sel] * k + tw[sel]
+    v = vals[sel].astype(F32)
+    order = np.argsort(key, kind="stable")
+    key_s, v_s = key[order], v[order]
+    uniq, start = np.unique(key_s, return_index=True)
+    sums = np.zeros(len(uniq), dtype=F32)
+    pos = start.copy()
+    end = np.concatenate([start[1:], [len(key_s)]])
+    live = np.arange(len(uniq))
+    while len(live):                                   # add the i-th value of every (doc, topic) run in lock step
+        sums[live] = (sums[live] + v_s[pos[live]]).astype(F32)
+        pos[live] += 1
+        live = live[pos[live] < end[live]]
+    nzm = sums != 0
+    dts_doc, dts_topic, dts_val = (uniq[nzm] // k).astype(np.int64), (uniq[nzm] % k).astype(np.int64), sums[nzm]
+    # top two topics per document (strict >, topic order)
+    pairs = []
+    bounds = np.searchsorted(dts_doc, np.arange(D + 1))
+    for d in range(D):
+        mx = mx2 = F32(0.0)
+        t1 = t2 = -1
+        for i in range(bounds[d], bounds[d + 1]):
+            x = dts_val[i]
+            if x > mx:
+                mx2, t2 = mx, t1
+                mx, t1 = x, int(dts_topic[i])
+            elif x > mx2:
+                mx2, t2 = x, int(dts_topic[i])
+        if t1 >= 0 and t2 >= 0:
+            pairs.append((t1, t2, d))
+    rank = int(np.uint64(eps3 * w0 * float(F32(D)) / (float(F32(k)) * 2.0)))
+    thr = np.zeros(k, dtype=F32)
+    for t in range(k):
+        if len(catchwords[t]) > 0:
+            x = np.sort(dts_val[dts_topic == t])[::-1]
+            if len(x) >= rank and rank >= 1:
+                thr[t] = x[rank - 1]
+    Model = np.zeros((V, k), dtype=F32)
+    cl = np.asarray(cluster_of_doc).astype(np.int64)
+    # additions in document order: first the document's qualifying (doc, topic) entries in topic order, then its own cluster
+    add_doc = np.concatenate([dts_doc[dts_val > thr[dts_topic]], np.nonzero(cl != 0xFFFFFFFF)[0]])
+    add_topic = np.concatenate([dts_topic[dts_val > thr[dts_topic]], cl[cl != 0xFFFFFFFF]])
+    add_second = np.concatenate([np.zeros(int((dts_val > thr[dts_topic]).sum()), np.int64), np.ones(int((cl != 0xFFFFFFFF).sum()), np.int64)])
+    o = np.lexsort((add_topic, add_second, add_doc))
+    add_doc, add_topic = add_doc[o], add_topic[o]
+    for t in range(k):
+        docs = add_doc[add_topic == t]
+        if len(docs) == 0:
+            continue
+        ln = lens[docs]
+        idx = np.repeat(offsets[docs], ln) + (np.arange(ln.sum()) - np.repeat(np.cumsum(ln) - ln, ln))
+        col = np.zeros(V, dtype=F32)
+        np.add.at(col, rows[idx].astype(np.int64), vals[idx].astype(F32))      # unbuffered, in index order, fp32
+        Model[:, t] = col
+    s = np.abs(Model).sum(0, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        Model = (Model * (F32(1.0) / s.astype(F32))[None, :]).astype(F32)
+    return Model, (dts_doc, dts_topic, dts_val), np.array(pairs, dtype=np.int64).reshape(-1, 3), thr
+
+
 # --------------------------------------------------------------------------- comparisons
 def principal_angle_sin(U1, U2):
     """sin of the largest principal angle between span(U1) and span(U2) (orthonormal cols)."""

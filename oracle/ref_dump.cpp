@@ -16,13 +16,14 @@
  *   stage E  run_lloyds_on_projected_space + left_multiply_by_U_Spectra (:546-550)
  *   stage F  run_lloyds on the full-dimensional B   (:559-571)
  *   stage G  rth_highest_element per cluster + find_catchwords   (:573-639)
+ *   stage H  construct_topic_model                                (:645-651)
  *
  * Input : <corpus.bin>  = int64 V, D, nnz ; int64 offsets[D+1] ; uint32 rows[nnz] ;
  *                         uint32 counts[nnz]      (doc-major CSC of raw counts)
  * Output: <outdir>/<name>.bin raw little-endian arrays + meta.json with sizes and
  *         per-stage wall-clock seconds (used as the CPU baseline by bench.py).
  *
- * usage: ref_dump <corpus.bin> <outdir> <k> [--upto A|B|C|D|E|F|G] [--mask mask.u8]
+ * usage: ref_dump <corpus.bin> <outdir> <k> [--upto A|B|C|D|E|F|G|H] [--mask mask.u8]
  *                 [--centers centers_lowd.f32]   (override k-means++ seeds for Lloyd)
  *                 [--lloyd-iters n] [--srand seed]
  */
@@ -36,6 +37,8 @@
 
 #include "sparseMatrix.h"
 #include "hyperparams.h"
+#include "denseMatrix.h"
+#include <tuple>
 
 using namespace ISLE;
 
@@ -94,7 +97,7 @@ int main(int argc, char **argv)
     }
     const std::string corpus = argv[1], out = argv[2];
     const doc_id_t k = (doc_id_t)std::atol(argv[3]);
-    char upto = 'G';
+    char upto = 'H';
     std::string mask_file, centers_file;
     int lloyd_iters = MAX_KMEANS_LOWD_REPS;
     for (int i = 4; i < argc; ++i) {
@@ -286,9 +289,36 @@ int main(int argc, char **argv)
             for (auto w : catchwords[c]) { pairs.push_back((uint32_t)c); pairs.push_back((uint32_t)w); }
         dump(out, "catchwords", pairs.data(), pairs.size());
     }
+    std::fprintf(meta, ", \"catch_r\": %llu, \"t_catchwords\": %.6f", (unsigned long long)r, t_cw);
+    if (upto == 'G') { delete[] catchwords; delete[] closest_full; std::fprintf(meta, "}\n"); std::fclose(meta); return 0; }
+
+    /* ---- stage H: topic model (trainer.cpp:645-651) ---- */
+    t0 = now_s();
+    DenseMatrix<FPTYPE> Model((word_id_t)V, (doc_id_t)k);
+    std::vector<std::tuple<int, int, doc_id_t> > top_topic_pairs;
+    std::vector<std::pair<word_id_t, int> > catchword_topics;
+    std::vector<std::tuple<doc_id_t, doc_id_t, FPTYPE> > doc_topic_sum;
+    A_sp->construct_topic_model(Model, k, closest_full, catchwords, AVG_CLUSTER_FOR_CATCHLESS_TOPIC,
+                                &top_topic_pairs, &catchword_topics, &doc_topic_sum);
+    double t_tm = now_s() - t0;
+    {
+        dump(out, "model", Model.data(), (size_t)V * (size_t)k);
+        std::vector<uint32_t> dts_doc, dts_topic, ttp;
+        std::vector<float> dts_val;
+        for (auto &e : doc_topic_sum) {
+            dts_doc.push_back((uint32_t)std::get<0>(e)); dts_topic.push_back((uint32_t)std::get<1>(e)); dts_val.push_back(std::get<2>(e));
+        }
+        for (auto &e : top_topic_pairs) {
+            ttp.push_back((uint32_t)std::get<0>(e)); ttp.push_back((uint32_t)std::get<1>(e)); ttp.push_back((uint32_t)std::get<2>(e));
+        }
+        dump(out, "dts_doc", dts_doc.data(), dts_doc.size());
+        dump(out, "dts_topic", dts_topic.data(), dts_topic.size());
+        dump(out, "dts_val", dts_val.data(), dts_val.size());
+        dump(out, "top_topic_pairs", ttp.data(), ttp.size());
+    }
     delete[] catchwords;
     delete[] closest_full;
-    std::fprintf(meta, ", \"catch_r\": %llu, \"t_catchwords\": %.6f}\n", (unsigned long long)r, t_cw);
+    std::fprintf(meta, ", \"t_topic_model\": %.6f}\n", t_tm);
     std::fclose(meta);
     delete B;
     delete A_sp;

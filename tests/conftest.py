@@ -50,6 +50,16 @@ def golden_c1_stageG():
 
 
 @pytest.fixture(scope="session")
+def golden_tiny_stageH():
+    return dict(np.load(os.path.join(GOLDEN, "tiny_stageH.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_c1_stageH():
+    return dict(np.load(os.path.join(GOLDEN, "c1_stageH.npz")))
+
+
+@pytest.fixture(scope="session")
 def corpus_c1():
     from isle_b200 import corpus
     return corpus.generate("c1")

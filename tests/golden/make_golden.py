@@ -78,6 +78,22 @@ def stage_g(name):
                 catchwords=ld("catchwords", np.uint32).reshape(-1, 2))
 
 
+def stage_h(name):
+    """Stage H (construct_topic_model): what went in (partition, catchwords) and what came out
+    (Model V x k, the (doc, topic, sum) list, the top topic pairs)."""
+    c, tmp, out, ld = run(name)
+    return dict(corpus_sha=out["corpus_sha"], A_vals_sha=out["A_vals_sha"],
+                cluster_of_doc=ld("catch_cluster_of_doc", np.uint32), catchwords=ld("catchwords", np.uint32).reshape(-1, 2),
+                model=ld("model", np.float32), dts_doc=ld("dts_doc", np.uint32), dts_topic=ld("dts_topic", np.uint32),
+                dts_val=ld("dts_val", np.float32), top_topic_pairs=ld("top_topic_pairs", np.uint32).reshape(-1, 3))
+
+
+def main_stage_h():
+    here = os.path.dirname(__file__)
+    for name in ("tiny", "c1"):
+        np.savez_compressed(os.path.join(here, f"{name}_stageH.npz"), **stage_h(name))
+
+
 def main_stage_f():
     here = os.path.dirname(__file__)
     for name in ("tiny", "c1"):
@@ -95,6 +111,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--stage-g" in sys.argv:
         main_stage_g()
+        sys.exit(0)
+    if "--stage-h" in sys.argv:
+        main_stage_h()
         sys.exit(0)
     here = os.path.dirname(__file__)
     c, tmp, out, ld = run("tiny")
@@ -122,3 +141,4 @@ if __name__ == "__main__":
 
     main_stage_f()
     main_stage_g()
+    main_stage_h()

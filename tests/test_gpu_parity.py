@@ -488,6 +488,45 @@ def test_rth_highest_element_edges(ctx):
     assert all(len(x) == 0 for x in A.find_catchwords(1, thr[:1]))   # k = 1: the reference's loop never sets the flag
 
 
+@pytest.mark.parametrize("name", ["tiny", "c1"])
+def test_topic_model_matches_reference(ctx, name, golden_tiny_stageH, golden_c1_stageH, corpus_c1):
+    """SURVEY 8(f) row 2, second half (construct_topic_model, src/sparseMatrix.cpp:597-838) through the C ABI against
+    the reference's own output: (doc, topic, sum) list and top topic pairs bit-exact, model within 1e-6."""
+    from isle_b200 import corpus
+    g = golden_tiny_stageH if name == "tiny" else golden_c1_stageH
+    c = corpus.generate("tiny") if name == "tiny" else corpus_c1
+    A, vals = _upload_A(ctx, c)
+    cw = [g["catchwords"][g["catchwords"][:, 0] == t, 1].astype(np.int64) for t in range(c.k)]
+    M, (dd, dt, dv), pairs = A.construct_topic_model(c.k, g["cluster_of_doc"], cw)
+    assert np.array_equal(dd, g["dts_doc"]) and np.array_equal(dt, g["dts_topic"])
+    assert np.array_equal(dv.view(np.uint32), g["dts_val"].view(np.uint32))
+    assert np.array_equal(pairs, g["top_topic_pairs"].astype(np.int64))
+    M_ref = g["model"].reshape(c.k, c.V).T
+    assert np.max(np.abs(M - M_ref)) <= 1e-6 * np.max(np.abs(M_ref))
+    assert np.allclose(M.sum(0), 1.0, atol=1e-5)
+
+
+def test_topic_model_corner_cases(ctx):
+    """Topics without catchwords, documents in no cluster, an empty cluster and a topic nobody contributes to (its
+    column divides by zero, as the reference's FPscal(1 / asum) does), against the oracle."""
+    from isle_b200 import corpus
+    c = corpus.generate("tiny")
+    A, vals = _upload_A(ctx, c)
+    rng = np.random.default_rng(4)
+    k = 6
+    cl = rng.integers(0, 5, c.D).astype(np.uint32)               # cluster 5 stays empty
+    cl[rng.random(c.D) < 0.1] = 0xFFFFFFFF
+    words = rng.permutation(c.V)
+    cw = [np.sort(words[:40]), np.sort(words[40:45]), np.zeros(0, np.int64), np.sort(words[45:300]), np.zeros(0, np.int64),
+          np.zeros(0, np.int64)]
+    M, (dd, dt, dv), pairs = A.construct_topic_model(k, cl, cw)
+    M_o, (dd_o, dt_o, dv_o), pairs_o, _ = O.construct_topic_model(vals, c.rows, c.offsets, c.V, k, cl, cw)
+    assert np.array_equal(dd, dd_o) and np.array_equal(dt, dt_o) and np.array_equal(dv.view(np.uint32), dv_o.view(np.uint32))
+    assert np.array_equal(pairs, pairs_o)
+    assert np.all(np.isnan(M[:, 5])) and np.all(np.isnan(M_o[:, 5]))      # 0 * (1 / 0)
+    assert np.max(np.abs(M[:, :5] - M_o[:, :5])) <= 1e-6 * np.max(np.abs(M_o[:, :5]))
+
+
 # ---------------------------------------------------------------- end to end
 def test_spectral_core_end_to_end_c1(ctx, golden_c1, corpus_c1):
     """Stages A-E through the public call; k-means is checked through rotation-invariant

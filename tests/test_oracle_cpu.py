@@ -226,6 +226,25 @@ def test_catchwords_match_reference(name, golden_tiny_stageG, golden_c1_stageG, 
     assert np.array_equal(pairs, g["catchwords"])
 
 
+@pytest.mark.parametrize("name", ["tiny", "c1"])
+def test_topic_model_matches_reference(name, golden_tiny_stageH, golden_c1_stageH, corpus_c1):
+    """SURVEY 8(f) row 2, second half: construct_topic_model restated against the reference's own output
+    (tests/golden/*_stageH.npz, made by ref_dump stage H): the (doc, topic, sum) list and the top topic pairs
+    bit-exact, the model to fp32 rounding."""
+    from isle_b200 import corpus
+    g = golden_tiny_stageH if name == "tiny" else golden_c1_stageH
+    c = corpus.generate("tiny") if name == "tiny" else corpus_c1
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    cw = [g["catchwords"][g["catchwords"][:, 0] == t, 1].astype(np.int64) for t in range(c.k)]
+    M, (dd, dt, dv), pairs, _ = O.construct_topic_model(vals, c.rows, c.offsets, c.V, c.k, g["cluster_of_doc"], cw)
+    assert np.array_equal(dd, g["dts_doc"]) and np.array_equal(dt, g["dts_topic"])
+    assert np.array_equal(dv.view(np.uint32), g["dts_val"].view(np.uint32))
+    assert np.array_equal(pairs, g["top_topic_pairs"].astype(np.int64))
+    M_ref = g["model"].reshape(c.k, c.V).T
+    assert np.max(np.abs(M - M_ref)) <= 1e-6 * np.max(np.abs(M_ref))
+    assert np.allclose(M_ref.sum(0), 1.0, atol=1e-5)
+
+
 def test_rth_highest_element_edges():
     """Branches of src/sparseMatrix.cpp:496-520: empty cluster, count == r (not > r), r >= cluster size."""
     offsets = np.array([0, 2, 4, 5], dtype=np.int64)
