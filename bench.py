@@ -145,6 +145,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_tf32_peak():
+    """Dense TF32 tensor-pipe peak in TFLOP/s: half the measured bf16 burst figure (no TF32 entry is measured)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if d.get("bf16_tflops"):
+            return 0.5 * float(d["bf16_tflops"]), "measured bf16 burst / 2 (MEASURED_PEAKS.json)"
+    return 0.5 * 2250.0, "nominal bf16 / 2"
+
+
 def load_traffic(config):
     """DRAM bytes per SpMM pass from the committed ncu --set full capture (profiles/spmm_traffic.json)."""
     p = os.path.join(ROOT, "profiles", "spmm_traffic.json")
@@ -424,6 +434,14 @@ def bench_ours(args):
                          "peak_source": peak_src, "launches": int(ncalls),
                          "avg_launch_ms": spmm_ms / ncalls if ncalls else None,
                          "bytes_per_launch": spmm_bytes / ncalls if ncalls else None},
+            # the one dense contraction of the path (docs x centers distances, Lloyd assignment passes): logical flops
+            # 2 D_B k k per pass; the tensor pipe does 3x that (split TF32: hi*hi + hi*lo + lo*hi)
+            "tensor": (lambda pk: {"kernel": "dist_tc_kernel (tcgen05 kind::tf32, split TF32)", "bound": "tensor",
+                                   "logical_tflops": st["dist_tc_flops"] / (st["dist_tc_ms"] * 1e-3) / 1e12 if st["dist_tc_ms"] else None,
+                                   "pipe_tflops": 3.0 * st["dist_tc_flops"] / (st["dist_tc_ms"] * 1e-3) / 1e12 if st["dist_tc_ms"] else None,
+                                   "peak": pk[0], "unit": "TFLOP/s", "peak_source": pk[1],
+                                   "frac": (3.0 * st["dist_tc_flops"] / (st["dist_tc_ms"] * 1e-3) / 1e12 / pk[0]) if st["dist_tc_ms"] else None})(
+                load_tf32_peak()),
             "stage_ms_per_step": {n[:-3]: st[n] / args.steps for n in st if n.endswith("_ms")},
             # block Gram-Schmidt panel products: algorithmic bytes (n x rows x 4 per product) of the passes that ran
             # (elided third passes return at once and move nothing) / CUDA-event time, reduce kernels included
