@@ -143,6 +143,7 @@ void thresholds_device(Ctx &c, uint32_t k, uint32_t r, const uint32_t *doc_ids, 
     const uint32_t V = (uint32_t)c.V;
     const size_t nkeys = (size_t)k * V;
     ISLE_CUDA_CHECK(cudaMemsetAsync(thr, 0, nkeys * sizeof(float), c.stream));
+    c.counters["cw_candidates"] = 0.0;
     if (!ndocs) return;
     DevBuf<uint32_t> count(nkeys), cl_size(k), flag(nkeys), take(nkeys), slot(nkeys);
     DevBuf<int64_t> voff(nkeys + 1);
