@@ -74,6 +74,13 @@ int isle_cuda_build_B(isle_cuda_ctx *ctx, const uint8_t *select_docs_or_null,
 /* Per-document importance-sampling weights, sum of zeta_w over kept entries
  * (src/sparseMatrix.cpp:1383-1397); weights_out: D floats. */
 int isle_cuda_sampling_weights(isle_cuda_ctx *ctx, float *weights_out);
+/* SURVEY 8(f) row 4.  The selection of sampled_threshold_and_copy (src/sparseMatrix.cpp:1399-1415) on the device:
+ * key_d = u_d^(1 / weight_d) (0 when the weight is 0) with u_d a counter-based uniform of (seed, d) in place of the
+ * reference's racy libc rand(); select_out[d] = 1 for the documents whose key is at least the (floor(rate D) + 1)-th
+ * largest (all of them when floor(rate D) >= D); *n_selected_out (may be NULL) = how many.  Pass select_out to
+ * isle_cuda_build_B.  Single-GPU contexts. */
+int isle_cuda_sample_docs(isle_cuda_ctx *ctx, float sample_rate, uint64_t seed, uint8_t *select_out,
+                          uint64_t *n_selected_out);
 /* Copies B back in the reference's layout for the host stages that follow the spectral
  * core (vals f32[nnz_B], rows u64[nnz_B], offsets i64[D_B+1], original_cols u64[D_B]).
  * Any pointer may be NULL to skip that array. */

@@ -270,6 +270,11 @@ int isle_cuda_lloyd_full(isle_cuda_ctx *h, uint64_t k, float *centers_inout, int
     });
 }
 
+int isle_cuda_sample_docs(isle_cuda_ctx *h, float sample_rate, uint64_t seed, uint8_t *select_out, uint64_t *n_selected_out)
+{
+    return guarded(h, [&](Ctx &c) { sample_docs(c, sample_rate, seed, select_out, n_selected_out); });
+}
+
 int isle_cuda_catchword_thresholds(isle_cuda_ctx *h, uint64_t k, uint64_t r, const uint32_t *cluster_of_doc, float *thresholds_out)
 {
     return guarded(h, [&](Ctx &c) { catchword_thresholds(c, k, r, cluster_of_doc, thresholds_out); });

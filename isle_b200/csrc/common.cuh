@@ -306,6 +306,7 @@ void upload_A(Ctx &c, uint64_t V, uint64_t D, int64_t nnz, const float *vals, co
 void compute_thresholds(Ctx &c, uint64_t k, float *zetas_out, int64_t *new_nnz_out);
 void build_B(Ctx &c, const uint8_t *select, int64_t *nnzB, uint64_t *DB);
 void sampling_weights(Ctx &c, float *out);
+void sample_docs(Ctx &c, float sample_rate, uint64_t seed, uint8_t *select_out, uint64_t *n_selected_out);
 void download_B(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets, uint64_t *orig);
 float frobenius(Ctx &c);
 

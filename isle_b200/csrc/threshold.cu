@@ -380,6 +380,72 @@ void sampling_weights(Ctx &c, float *out)
     ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }
 
+// ----------------------------------------------------------------- importance sampling of documents
+// sampled_threshold_and_copy (src/sparseMatrix.cpp:1383-1415), SURVEY 8(f) row 4: weight_d = sum of zeta over the kept
+// entries of document d; key_d = u_d^(1 / weight_d) (0 when the weight is 0); keep the documents whose key is at least the
+// (floor(rate D) + 1)-th largest (A-Res weighted reservoir sampling).  The reference draws u from libc rand() inside a
+// parallel loop (racy); here u_d is a counter-based uniform of (seed, d), so the selection is reproducible
+// and independent of the launch geometry.
+__device__ __forceinline__ uint64_t sample_mix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+sample_keys_kernel(const float *__restrict__ w, uint32_t D, uint64_t seed, float *__restrict__ key)
+{
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const float u = (float)(sample_mix64(seed ^ sample_mix64((uint64_t)d)) >> 40) * (1.0f / 16777216.0f);     // [0, 1), 24 bits
+    const float wd = w[d];
+    key[d] = wd == 0.0f ? 0.0f : powf(u, 1.0f / wd);
+}
+
+__global__ void __launch_bounds__(256)
+sample_select_kernel(const float *__restrict__ key, uint32_t D, const float *__restrict__ sorted_desc, uint32_t nth,
+                     uint8_t *__restrict__ select, uint32_t *__restrict__ n_selected)
+{
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool keep = d < D && (nth >= D || key[d] >= sorted_desc[nth]);      // :1410-1415 (pivot = dice[nth])
+    if (d < D) select[d] = keep ? 1 : 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_selected, (uint32_t)__popc(m));
+}
+
+void sample_docs(Ctx &c, float sample_rate, uint64_t seed, uint8_t *select_out, uint64_t *n_selected_out)
+{
+    ISLE_REQUIRE(c.have_zeta, ISLE_ERR_ARG, "sample_docs: compute thresholds first");
+    ISLE_REQUIRE(sample_rate >= 0.0f && select_out, ISLE_ERR_ARG, "sample_docs: bad arguments");
+    ISLE_REQUIRE(c.world == 1, ISLE_ERR_ARG, "sample_docs: single-GPU contexts only (the pivot is a global order statistic)");
+    const uint32_t D = (uint32_t)c.D;
+    if (n_selected_out) *n_selected_out = 0;
+    if (!D) return;
+    DevBuf<uint32_t> cnt(D), nsel(1);
+    DevBuf<float> w(D), key(D), sorted(D);
+    DevBuf<uint8_t> sel(D);
+    count_kept_kernel<<<grid_for((size_t)D * 32, 256, c.num_sms * 16), 256, 0, c.stream>>>(c.a_val.p, c.a_row.p, c.a_off.p, D, c.zeta.p,
+                                                                                      nullptr, cnt.p, w.p);
+    sample_keys_kernel<<<(D + 255) / 256, 256, 0, c.stream>>>(w.p, D, seed, key.p);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortKeysDescending(nullptr, tb, key.p, sorted.p, (int)D, 0, 32, c.stream);
+    DevBuf<uint8_t> tmp(tb);
+    ISLE_CUDA_CHECK(cub::DeviceRadixSort::SortKeysDescending(tmp.p, tb, key.p, sorted.p, (int)D, 0, 32, c.stream));
+    // nth = (size_t)(sample_rate * (float)D)   (:1406)
+    const float nth_f = sample_rate * (float)D;
+    const uint32_t nth = nth_f >= (float)D ? D : (uint32_t)nth_f;
+    ISLE_CUDA_CHECK(cudaMemsetAsync(nsel.p, 0, 4, c.stream));
+    sample_select_kernel<<<(D + 255) / 256, 256, 0, c.stream>>>(key.p, D, sorted.p, nth, sel.p, nsel.p);
+    count_launch(c, 4);
+    uint32_t h = 0;
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(select_out, sel.p, D, cudaMemcpyDeviceToHost, c.stream));
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(&h, nsel.p, 4, cudaMemcpyDeviceToHost, c.stream));
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    if (n_selected_out) *n_selected_out = h;
+}
+
 // ---------------------------------------------------------------------------- download B
 __global__ void expand_B_kernel(const uint32_t *__restrict__ b_row, const float *__restrict__ sqrt_zeta,
                                 int64_t n, float *__restrict__ vals, unsigned long long *__restrict__ rows)

@@ -179,11 +179,17 @@ class FPSparseMatrix:
 
     def sampled_threshold_and_copy(self, A: SparseMatrix, zetas, nnzs: int, sample_rate: float,
                                    rng: Optional[np.random.Generator] = None,
-                                   select_docs: Optional[np.ndarray] = None) -> np.ndarray:
+                                   select_docs: Optional[np.ndarray] = None,
+                                   device_seed: Optional[int] = None) -> np.ndarray:
         """src/sparseMatrix.cpp:1365-1435.  weight_d = sum zeta over kept entries (device);
         key_d = u^(1/weight_d); keep the floor(rate*D) largest keys (A-Res sampling).  The
         reference draws u from libc rand() inside a parallel loop (racy); here the
         caller supplies the generator, or the selection mask itself for parity runs."""
+        if select_docs is None and device_seed is not None:      # keys, pivot and selection on the device
+            select_docs = np.zeros(A.num_docs(), dtype=np.uint8)
+            nsel = C.c_uint64()
+            self.ctx.call("isle_cuda_sample_docs", C.c_float(sample_rate), int(device_seed), ptr(select_docs), C.byref(nsel))
+            self.last_sample_count = int(nsel.value)
         if select_docs is None:
             w = np.zeros(A.num_docs(), dtype=np.float32)
             self.ctx.call("isle_cuda_sampling_weights", ptr(w))

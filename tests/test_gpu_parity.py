@@ -86,6 +86,50 @@ def test_sampling_weights(ctx, golden_tiny):
     assert np.array_equal(w, O.sampling_weights(g["A_normalized_vals"], g["rows"], g["offsets"], g["zetas"]))
 
 
+def test_sample_docs_on_device(ctx, golden_tiny):
+    """the A-Res selection of sampled_threshold_and_copy (src/sparseMatrix.cpp:1399-1415) on the device
+    against a numpy replay of the same counter-based uniforms; powf may differ from numpy in the last place, so keys
+    within a few ulps of the pivot may fall on either side."""
+    from isle_b200._capi import ptr
+    import ctypes as C
+    g = golden_tiny
+    A, B, zetas, nn, oc = tiny_AB(ctx, g)
+    D = int(g["D"])
+    w = np.zeros(D, np.float32)
+    ctx.call("isle_cuda_sampling_weights", ptr(w))
+
+    def mix(x):
+        x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+        x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)).astype(np.uint64)
+        x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)).astype(np.uint64)
+        return x ^ (x >> np.uint64(31))
+
+    for rate, seed in ((0.4, 7), (0.05, 8), (0.999, 9)):
+        sel = np.zeros(D, np.uint8)
+        nsel = C.c_uint64()
+        ctx.call("isle_cuda_sample_docs", C.c_float(rate), seed, ptr(sel), C.byref(nsel))
+        with np.errstate(over="ignore"):
+            u = (mix(np.uint64(seed) ^ mix(np.arange(D, dtype=np.uint64))) >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+        with np.errstate(divide="ignore"):
+            key = np.where(w == 0, np.float32(0), np.power(u, (np.float32(1) / w).astype(np.float32), dtype=np.float32)).astype(np.float32)
+        nth = int(np.float32(rate) * np.float32(D))
+        pivot = np.sort(key)[::-1][nth]
+        ref = key >= pivot
+        assert int(nsel.value) == int(sel.sum())
+        assert abs(int(sel.sum()) - int(ref.sum())) <= 2 and int((sel.astype(bool) != ref).sum()) <= 4
+        assert int(sel.sum()) >= nth + 1 - 2
+        # zero-weight documents are only kept when the pivot itself is 0
+        assert pivot == 0 or not np.any(sel.astype(bool) & (w == 0))
+    sel = np.zeros(D, np.uint8)
+    ctx.call("isle_cuda_sample_docs", C.c_float(1.0), 1, ptr(sel), None)      # floor(rate D) >= D: everything
+    assert sel.all()
+    # the masked build accepts the device selection (sampled_threshold_and_copy with device_seed)
+    from isle_b200.sparse_matrix import FPSparseMatrix
+    B2 = FPSparseMatrix(A)
+    oc2 = B2.sampled_threshold_and_copy(A, zetas, nn, 0.4, device_seed=7)
+    assert B2.num_docs() <= B2.last_sample_count and len(oc2) == B2.num_docs()
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_thresholds_ragged_edge_cases(ctx, seed):
     """Empty docs, absent words, one-word docs, values that round to zero, heavy ties."""
