@@ -675,11 +675,8 @@ struct PanelSimt {
             StatScope s(c, "ks_wtf", (double)n * rows * 4.0, 2.0 * (double)n * rows * cols);
             if (v2) {
                 const int smem = BP * 256 * (int)sizeof(float4);
-                static bool attr_set = false;       // one instantiation per BP: set once per process
-                if (!attr_set) {
-                    ISLE_CUDA_CHECK(cudaFuncSetAttribute(wtf_partial_v2_kernel<BP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                    attr_set = true;
-                }
+                // per launch, not once per process: the attribute is per device
+                ISLE_CUDA_CHECK(cudaFuncSetAttribute(wtf_partial_v2_kernel<BP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
                 dim3 g((rows + kWtf2Cols - 1) / kWtf2Cols, chunks);
                 wtf_partial_v2_kernel<BP><<<g, 512, smem, c.stream>>>(W, Fm, n, rows, cols, wpart.p);
             } else {

@@ -431,11 +431,8 @@ void launch_panel(Ctx &c, const CUtensorMap &ma, const CUtensorMap &mb, PanelPar
     p.stages = (uint32_t)std::max(2, std::min(10, c.opt("ks_panel_tc_stages", 8)));
     p.diag = c.head_diag_dev;
     const uint32_t smem_bytes = p.stages * kStageBytes + 1024 + 512;
-    static bool attr_set = false;
-    if (!attr_set) {
-        ISLE_CUDA_CHECK(cudaFuncSetAttribute(panel_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * kStageBytes + 1024 + 512));
-        attr_set = true;
-    }
+    // per launch, not once per process: the attribute is per device and a process may hold contexts on several
+    ISLE_CUDA_CHECK(cudaFuncSetAttribute(panel_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     const uint32_t njobs = p.num_mtiles * p.nseg;
     const unsigned grid = std::min<uint32_t>(njobs, (uint32_t)c.num_sms);
     panel_tc_kernel<MODE><<<grid, kThreads, smem_bytes, c.stream>>>(ma, mb, p);
