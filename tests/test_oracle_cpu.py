@@ -302,3 +302,26 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "isle_oracle" not in src and "oracle/" not in src.replace("oracle/ref_dump", ""), f
+
+
+def test_reference_side_binding_covers_every_member():
+    """The drop-in binary built by oracle/Makefile (reference CLI + trainer.cpp + the shim TU + libisle_cuda.so) must
+    bind every member INTEGRATION.md section 2 lists to the shim's strong definition, not to the reference's weak
+    template instantiation.  Skipped where oracle/_ref has not been built (no /root/reference)."""
+    import shutil
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "ISLETrain_cuda")
+    if not os.path.exists(exe) or not shutil.which("nm"):
+        pytest.skip("oracle/_ref/ISLETrain_cuda not built here")
+    syms = subprocess.run(["nm", "-C", exe], capture_output=True, text=True, check=True).stdout.splitlines()
+    strong = {ln.split(" ", 2)[2] for ln in syms if len(ln.split(" ", 2)) == 3 and ln.split(" ", 2)[1] == "T"}
+    members = ["SparseMatrix<float>::list_word_freqs_by_sorting(", "SparseMatrix<float>::compute_thresholds(",
+               "FPSparseMatrix<float>::threshold_and_copy<float>(", "FPSparseMatrix<float>::sampled_threshold_and_copy<float>(",
+               "FPSparseMatrix<float>::frobenius(", "FPSparseMatrix<float>::initialize_for_eigensolver(",
+               "FPSparseMatrix<float>::compute_block_ks(", "FPSparseMatrix<float>::cleanup_after_eigensolver(",
+               "FPSparseMatrix<float>::kmeans_init_on_projected_space(", "FPSparseMatrix<float>::run_lloyds_on_projected_space(",
+               "FPSparseMatrix<float>::left_multiply_by_U_Spectra(", "FPSparseMatrix<float>::run_lloyds(",
+               "SparseMatrix<float>::rth_highest_element(", "SparseMatrix<float>::find_catchwords(",
+               "SparseMatrix<float>::construct_topic_model("]
+    for m in members:
+        assert any(("ISLE::" + m) in s for s in strong), f"{m} is not bound to the shim"

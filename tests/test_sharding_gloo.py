@@ -1,7 +1,8 @@
 """world_size = 2 over gloo on CPU: the host-side logic of the document-sharded path and the
 algebra the device collectives rely on -- global ingest statistics from slices,
 per-word histograms that add across ranks to the single-process thresholds, B slices and the
-global column numbering, Lloyd center sums.  No GPU, no CUDA calls."""
+global column numbering, Lloyd center sums, the integer member counts of the full-dimensional Lloyd.
+No GPU, no CUDA calls."""
 import os
 import socket
 
@@ -83,6 +84,28 @@ def _worker(rank, world, port, golden_path, out):
         fs = np.zeros_like(sums); np.add.at(fs, a_full, P_full.astype(np.float64))
         assert np.array_equal(tc.numpy(), np.bincount(a_full, minlength=k))
         assert np.allclose(ts.numpy(), fs, rtol=1e-9, atol=1e-9)
+        # stage F (Lloyd on the full-dimensional B): assignments are local, integer member counts per (cluster, word)
+        # and cluster sizes add across ranks, so the centers built from the totals equal the single-process ones
+        gF = dict(np.load(os.path.join(os.path.dirname(golden_path), "tiny_stageF.npz")))
+        CF = gF["centers_in"].reshape(c.k, c.V)
+        aF_local = np.argmin(np.abs(O.dist_matrix_full(B_local, O.docs_l2sq_full(B_local), CF)), axis=1)
+        aF_full = np.argmin(np.abs(O.dist_matrix_full(B_full, O.docs_l2sq_full(B_full), CF)), axis=1)
+        assert np.array_equal(aF_local, aF_full[sel])
+
+        def member_counts(Bm, a):
+            import scipy.sparse as sp
+            M = sp.csr_matrix((np.ones(Bm.shape[1], np.int64), (np.arange(Bm.shape[1]), a)), shape=(Bm.shape[1], c.k))
+            return np.asarray(((Bm != 0).astype(np.int64) @ M).todense()).T.copy()          # [k, V]
+
+        tcnt = torch.from_numpy(member_counts(B_local, aF_local))
+        tsz = torch.from_numpy(np.bincount(aF_local, minlength=c.k).astype(np.int64))
+        dist.all_reduce(tcnt); dist.all_reduce(tsz)
+        assert np.array_equal(tcnt.numpy(), member_counts(B_full, aF_full))
+        assert np.array_equal(tsz.numpy(), np.bincount(aF_full, minlength=c.k))
+        sz = np.sqrt(z).astype(np.float32)
+        cen = np.where(tsz.numpy()[:, None] > 0, (sz[None, :] * tcnt.numpy().astype(np.float32)) / np.maximum(tsz.numpy(), 1)[:, None].astype(np.float32), 0)
+        C1, _ = O.lloyds_iter_full(B_full, O.docs_l2sq_full(B_full), CF)
+        assert np.max(np.abs(cen - C1)) <= 1e-5 * np.max(np.abs(C1))
         out[rank] = 1
     finally:
         dist.destroy_process_group()
