@@ -16,11 +16,17 @@ over one synthetic corpus.  At N=1 the corpus is BASELINE.json configs[1] (NYTim
             zetas, original_cols, eigenvalues and the lifted centers inside the timed region
   roofline  the B*B^T*X SpMM passes: algorithmic bytes / CUDA-event time, against
             the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  tensor    the one dense contraction of the path (docs x centers distances on tcgen05, split TF32):
+            logical and tensor-pipe TFLOP/s of the Lloyd assignment passes against the TF32 peak
   cpu_baseline  the UNMODIFIED reference C++ (oracle/_ref/ref_dump: reference sources over
             OpenBLAS + the MKL shim, not Intel MKL) on the host cores, on a bounded document
             slice of the same corpus
+  next_rows the stages widened from the spectral core (Lloyd on the full-dimensional B,
+            catchword thresholds + catchwords, topic model), timed beside the metric, not part of it
+  panel_gbs, stage_ms_per_step   where the step's time goes
 
---impl reference times only that CPU arm and prints the same line shape.
+--impl reference times only that CPU arm and prints the same line shape.  --config c3s runs one of the
+eight document shards of the PubMed-shaped c3 (k = 2000), the per-GPU workload of the 8 x B200 target.
 """
 from __future__ import annotations
 

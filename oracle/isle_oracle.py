@@ -1,6 +1,7 @@
 """oracle/isle_oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
-CPU restatement (numpy / scipy.sparse) of the reference's spectral core, the
+CPU restatement (numpy / scipy.sparse) of the reference's spectral core and of the stages
+widened from it (full-dimensional Lloyd, catchword thresholds, catchwords, topic model), the
 checker the CUDA path is compared against.  Only tests/, __graft_entry__.smoke()
 and bench.py's cpu_baseline leg may import this module; the product path
 (isle_b200/, libisle_cuda.so) never does.
