@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--cpu-sample-docs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--e2e-skip-B-U", dest="e2e_skip_B_U", action="store_true",
+                    help="e2e leg without the B / U downloads the reference-side shim makes (round-1 behaviour)")
     return ap.parse_args()
 
 
@@ -152,13 +154,57 @@ def load_peaks():
 
 
 def load_tf32_peak():
-    """Dense TF32 tensor-pipe peak in TFLOP/s: half the measured bf16 burst figure (no TF32 entry is measured)."""
+    """Fallback dense TF32 tensor-pipe peak in TFLOP/s when it cannot be measured in the run: half the measured bf16
+    burst figure."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
         if d.get("bf16_tflops"):
             return 0.5 * float(d["bf16_tflops"]), "measured bf16 burst / 2 (MEASURED_PEAKS.json)"
     return 0.5 * 2250.0, "nominal bf16 / 2"
+
+
+def measure_tf32_peak():
+    """Dense TF32 peak measured the way MEASURED_PEAKS.json measured bf16: torch.matmul fp32 with allow_tf32 on
+    8192^3, best of 10, CUDA events (library GEMM, outside every timed region)."""
+    try:
+        import torch
+        n = 8192
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(n, n, device="cuda", dtype=torch.float32)
+        b = torch.randn(n, n, device="cuda", dtype=torch.float32)
+        for _ in range(3):
+            torch.matmul(a, b)
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12, "measured in this run: torch.matmul fp32 allow_tf32 8192^3, best of 10 (burst)"
+    except Exception:
+        return load_tf32_peak()
+
+
+def corpus_sha16(c):
+    import hashlib
+    h = hashlib.sha256()
+    for a in (c.offsets, c.rows, c.counts):
+        h.update(np.ascontiguousarray(a).view(np.uint8).data)
+    return h.hexdigest()[:16]
+
+
+def workload_config(name, D, V, nnz, k, sha16=None):
+    """The `config` object both arms print (identical for the same corpus): what is computed, nothing about how."""
+    return {"workload": f"{name} {SHAPES.get(name, 'synthetic')} per GPU: {D} docs x {V} vocab, {nnz} nnz, k={k}",
+            "block_size": 10, "tol": 1e-4, "l2": "inputs (A: %.0f MB) larger than the 126 MB L2" % (nnz * 8 / 1e6),
+            "corpus_sha16": sha16}
 
 
 def load_traffic(config):
@@ -219,40 +265,138 @@ def pinned(a: np.ndarray) -> np.ndarray:
 
 
 # ------------------------------------------------------------------------------- reference arm
+REF_WALL_BUDGET_S = 150.0        # wall-clock budget of the reference arm's repetitions (corpus generation excluded)
+REF_MAX_FULL_NNZ = 120_000_000   # corpora above this (the k = 2000 shapes) cannot finish on the host cores in minutes
+
+
+def reference_line(args, cfg_name, D, V, nnz, k, ncores, times_s, docs_timed, reps_run, warmup_run, same_corpus, note, sha16=None):
+    """The JSON line of the reference arm (pure: tested on CPU)."""
+    t = float(np.mean(times_s))
+    val = docs_timed / t
+    sample = (f"{'the identical corpus of the GPU arm' if same_corpus else 'a document slice of the GPU arm corpus'}: "
+              f"{docs_timed} docs, V={V}, k={k}, stages A-E (thresholds, B, block-KS, k-means++, Lloyd on the projection), "
+              f"{reps_run} timed repetition(s) + {warmup_run} warm-up within a {REF_WALL_BUDGET_S:.0f} s wall budget; "
+              f"unmodified reference C++ over OpenBLAS + MKL shim (not Intel MKL); stage seconds from ref_dump's own "
+              f"stopwatch around the same calls the reference's timerLog.txt phases bracket{note}")
+    return {
+        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": workload_config(cfg_name, D, V, nnz, k, sha16),
+        "same_corpus_as_gpu_arm": bool(same_corpus), "reps_run": reps_run, "warmup_run": warmup_run,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
 def bench_reference(args):
+    """Times the reference's own CPU path on the corpus the GPU arm uses: the same generator call (make_corpus with
+    rank 0's document seed), hence the identical (D, V, nnz, seed) object on the same box.  Repetitions are
+    whole runs of the spectral core; as many as fit the wall budget (at least one)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from isle_b200 import corpus
     ncores = os.cpu_count() or 1
     cfg = corpus.CONFIGS[args.config]
-    nsteps = args.steps + args.warmup
-    ndocs = args.cpu_sample_docs or max(4000, min(30000, int(30000 * 6 / max(nsteps, 1))))
-    ndocs = min(ndocs, cfg["D"])
-    c = corpus.generate(V=cfg["V"], D=ndocs, k=cfg["k"], mu=cfg["mu"], seed=cfg["seed"] + args.seed)
-    times = []
+    try:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    except Exception:
+        pass
+    c = make_corpus(args.config, 0, args.seed)
+    D_full, nnz_full = c.D, c.nnz
+    sha16 = corpus_sha16(c)
+    same = True
+    note = ""
+    if args.cpu_sample_docs or nnz_full > REF_MAX_FULL_NNZ or cfg["k"] > 500:
+        nd = args.cpu_sample_docs or max(4 * cfg["k"], min(c.D, 30000))
+        c = slice_corpus(c, nd)
+        same = c.D == D_full
+        note = "" if same else f"; the full corpus ({D_full} docs, k={cfg['k']}) does not finish on the host cores in minutes"
+    if args.gpus > 1:
+        note += f"; N={args.gpus}: one rank's shard timed, docs/s of the host is what is reported"
+    times, warm = [], 0
+    t_begin = time.perf_counter()
     with tempfile.TemporaryDirectory(prefix="isle_ref_") as wd:
-        for i in range(nsteps):
+        core, wall, meta = run_ref_dump(c, cfg["k"], ncores, wd)
+        first_wall = wall
+        # the first run counts as warm-up only when another one fits the budget
+        if args.warmup > 0 and (time.perf_counter() - t_begin) + first_wall <= REF_WALL_BUDGET_S:
+            warm = 1
+        else:
+            times.append(core)
+        while len(times) < max(args.steps, 1) and ((time.perf_counter() - t_begin) + first_wall <= REF_WALL_BUDGET_S or not times):
             core, wall, meta = run_ref_dump(c, cfg["k"], ncores, wd)
-            if i >= args.warmup:
-                times.append(core)
-    t = float(np.mean(times))
-    val = ndocs / t
-    sample = (f"{ndocs}-doc corpus of the {args.config} shape (V={cfg['V']}, k={cfg['k']}, "
-              f"{c.nnz} nnz), stages A-E, reference C++ over OpenBLAS + MKL shim (not Intel MKL)")
-    line = {
-        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"{args.config}: {cfg['D']} docs x {cfg['V']} vocab, k={cfg['k']}", "sample_docs": ndocs},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "reference", "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
+            times.append(core)
+    line = reference_line(args, args.config, D_full, cfg["V"], nnz_full, cfg["k"], ncores, times, c.D, len(times), warm, same, note, sha16)
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------- our arm
+STAT_NAMES = ("launches", "spmm_bt_ms", "spmm_bt_bytes", "spmm_bt_calls", "spmm_b_ms", "spmm_b_bytes", "spmm_b_calls",
+              "ks_op_ms", "ks_orth_ms", "ks_qr_ms", "ks_truncate_ms", "ks_restarts", "ks_gs_elided", "ks_ops", "project_ms",
+              "lloyd_iter_ms", "pp_round_ms", "thr_hist_ms", "thr_zeta_ms", "b_count_ms", "b_compact_ms", "csr_build_ms",
+              "dist_tc_ms", "dist_simt_ms", "dist_tc_flops", "dist_simt_flops", "lloyd_accum_ms", "ks_wtf_ms", "ks_wtf_bytes",
+              "ks_wtfred_ms", "ks_fsub_ms", "ks_fsub_bytes", "pp_dist_tc_ms", "pp_dist_skinny_ms", "pp_dist_simt_ms",
+              "split_p_ms", "spmm_head1_ms", "spmm_tail1_ms", "spmm_head2_ms", "spmm_tail2_ms", "spmm_head_words",
+              "spmm_tail_nnz", "alloc_misses", "alloc_hits", "allreduce_ms", "lift_ms", "ks_evd_ms")
+
+
+def ours_line(*, args, world, cfg_name, D, V, nnz, k, sha16, total_docs, dev_ms, e2e_s, h2d, d2h, st, state, clocks,
+              hbm_peak, tf32_peak, traffic, step_wall, next_rows):
+    """The JSON line of our arm from the measured numbers (pure: tested on CPU with synthetic stats)."""
+    peak, peak_src = hbm_peak
+    spmm_ms = st["spmm_bt_ms"] + st["spmm_b_ms"]
+    spmm_bytes = st["spmm_bt_bytes"] + st["spmm_b_bytes"]
+    ach = spmm_bytes / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
+    ncalls = st["spmm_bt_calls"] + st["spmm_b_calls"]
+    tms, tfl = st["dist_tc_ms"], st["dist_tc_flops"]
+    pipe = 3.0 * tfl / (tms * 1e-3) / 1e12 if tms else None
+    live = 1.0 - (st["ks_gs_elided"] * args.steps) / max(3.0 * st["ks_ops"], 1.0)
+    return {
+        "metric": METRIC, "value": total_docs * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg_name, D, V, nnz, k, sha16),
+        # what the run did with that workload (kept out of `config`, which both arms print identically)
+        "run": {"D_B": state["DB"], "nnz_B": state["nnzB"], "ks_restarts": st["ks_restarts"],
+                "ks_block_steps": st["ks_ops"], "ks_gs_third_passes_elided": st["ks_gs_elided"],
+                "spmm_head_words": int(st["spmm_head_words"]), "spmm_tail_nnz": int(st["spmm_tail_nnz"]),
+                "lloyd_iters": state["iters"], "nconv": state["nconv"]},
+        # the e2e leg moves what the reference-side shim moves: A up (u64 row ids), zetas, all of B (vals, u64 rows,
+        # offsets, original_cols), eigenvalues, U, seeds, projected centers and the lifted centers down
+        "e2e": {"value": (total_docs * args.steps / e2e_s) if e2e_s and e2e_s != float("inf") else None, "unit": UNIT,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(st["launches"]),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "B^T X and B Y passes of the operator (spmm_head_kernel: tcgen05 dense head; "
+                                               "spmm_gather_bfp_kernel: tail)",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
+                     "traffic": traffic, "traffic_source": "stored ncu --set full capture (profiles/spmm_traffic.json), not measured in this run" if traffic else None,
+                     "peak_source": peak_src, "launches": int(ncalls),
+                     "avg_launch_ms": spmm_ms / ncalls if ncalls else None,
+                     "bytes_per_launch": spmm_bytes / ncalls if ncalls else None},
+        # the one dense contraction of the path (docs x centers distances, Lloyd assignment passes): logical flops
+        # 2 D_B k k per pass; the tensor pipe does 3x that (split TF32: hi*hi + hi*lo + lo*hi)
+        "tensor": {"kernel": "dist_tc_kernel (tcgen05 kind::tf32, split TF32)", "bound": "tensor",
+                   "logical_tflops": tfl / (tms * 1e-3) / 1e12 if tms else None, "pipe_tflops": pipe,
+                   "peak": tf32_peak[0], "unit": "TFLOP/s", "peak_source": tf32_peak[1],
+                   "frac": pipe / tf32_peak[0] if pipe else None},
+        "stage_ms_per_step": {n[:-3]: st[n] / args.steps for n in st if n.endswith("_ms")},
+        # block Gram-Schmidt panel products: algorithmic bytes (n x rows x 4 per product) of the passes that ran
+        # (elided third passes return at once and move nothing) / CUDA-event time, reduce kernels included
+        "panel_gbs": {"wtf": live * st["ks_wtf_bytes"] / st["ks_wtf_ms"] / 1e6 if st["ks_wtf_ms"] else None,
+                      "fsub": live * st["ks_fsub_bytes"] / st["ks_fsub_ms"] / 1e6 if st["ks_fsub_ms"] else None,
+                      "passes_run_fraction": live},
+        "step_wall_ms": [round(x, 2) for x in step_wall],
+        "next_rows": next_rows,
+        "alloc": {"driver_allocs_in_timed_region": st["alloc_misses"], "cache_hits_per_step": st["alloc_hits"] / args.steps},
+    }
+
+
 def bench_ours(args):
     import torch
     import torch.distributed as dist
@@ -279,6 +423,8 @@ def bench_ours(args):
     V, k = cfg["V"], cfg["k"]
     c = make_corpus(args.config, rank, args.seed)
     D, nnz = c.D, c.nnz
+    sha16 = corpus_sha16(c) if rank == 0 else None
+    tf32_peak = measure_tf32_peak() if rank == 0 else (None, None)
     # input normalisation = ISLETrainer's own ingest (populate_CSC + normalize_docs), outside the path;
     # avg_doc_sz is a statistic of the whole corpus, so shards exchange token / document totals
     avg, nz_local, _nz_global = sharding.global_doc_stats(c.counts, c.offsets)
@@ -288,11 +434,17 @@ def bench_ours(args):
     h_offs = pinned(c.offsets.astype(np.int64))
     torch.cuda.empty_cache()
 
-    zetas = np.zeros(V, np.float32)
+    zetas = pinned(np.zeros(V, np.float32))
     evalues = np.zeros(k, np.float32)
     seeds = np.zeros(k, np.uint64)
     centers_lowd = np.zeros((k, k), np.float32)
-    centers = np.zeros((k, V), np.float32)
+    centers = pinned(np.zeros((k, V), np.float32))
+    # host arrays the reference-side shim fills every run (threshold_and_copy: allocate(nnzs + 1000), U_colmajor)
+    full_dl = not args.e2e_skip_B_U
+    h_bvals = pinned(np.zeros(nnz + 1000, np.float32)) if full_dl else None
+    h_brows = pinned(np.zeros(nnz + 1000, np.uint64)) if full_dl else None
+    h_boffs = pinned(np.zeros(D + 1, np.int64)) if full_dl else None
+    h_U = pinned(np.zeros((k, V), np.float32)) if full_dl else None
     state = {}
 
     def upload():
@@ -305,8 +457,12 @@ def bench_ours(args):
         ctx.call("isle_cuda_build_B", None, C.byref(nnzB), C.byref(DB))
         if host_outputs:
             oc = np.zeros(int(DB.value), np.uint64)
-            ctx.call("isle_cuda_download_B", None, None, None, ptr(oc))
-        ctx.call("isle_cuda_block_ks", k, 10, 100, C.c_float(1e-4), step_seed, ptr(evalues), None, C.byref(nconv))
+            if full_dl:
+                ctx.call("isle_cuda_download_B", ptr(h_bvals), ptr(h_brows), ptr(h_boffs), ptr(oc))
+            else:
+                ctx.call("isle_cuda_download_B", None, None, None, ptr(oc))
+        ctx.call("isle_cuda_block_ks", k, 10, 100, C.c_float(1e-4), step_seed, ptr(evalues),
+                 ptr(h_U) if (host_outputs and full_dl) else None, C.byref(nconv))
         ctx.call("isle_cuda_kmeanspp", k, step_seed, ptr(seeds), ptr(centers_lowd), C.byref(res))
         ctx.call("isle_cuda_lloyd_projected", k, ptr(centers_lowd), 10, None, C.byref(obj), C.byref(iters))
         ctx.call("isle_cuda_lift_centers", k, ptr(centers_lowd), k, ptr(centers) if host_outputs else None)
@@ -343,14 +499,7 @@ def bench_ours(args):
     barrier()
     sampler.mark_end()
     dev_ms = ms.value
-    st = {n: ctx.stat(n) for n in ("launches", "spmm_bt_ms", "spmm_bt_bytes", "spmm_bt_calls", "spmm_b_ms",
-                                   "spmm_b_bytes", "spmm_b_calls", "ks_op_ms", "ks_orth_ms", "ks_qr_ms",
-                                   "ks_truncate_ms", "ks_restarts", "ks_gs_elided", "ks_ops", "project_ms", "lloyd_iter_ms", "pp_round_ms",
-                                   "thr_hist_ms", "thr_zeta_ms", "b_count_ms", "b_compact_ms", "csr_build_ms",
-                                   "dist_tc_ms", "dist_simt_ms", "dist_tc_flops", "dist_simt_flops", "lloyd_accum_ms",
-                                   "ks_wtf_ms", "ks_wtf_bytes", "ks_wtfred_ms", "ks_fsub_ms", "ks_fsub_bytes", "pp_dist_tc_ms",
-                                   "pp_dist_skinny_ms", "pp_dist_simt_ms", "split_p_ms", "spmm_head1_ms", "spmm_tail1_ms", "spmm_head2_ms", "spmm_tail2_ms", "spmm_head_words", "spmm_tail_nnz",
-                                   "alloc_misses", "alloc_hits")}
+    st = {n: ctx.stat(n) for n in STAT_NAMES}
     # ---- SURVEY 8(f) row 1, reported beside the metric (not part of it): Lloyd on the full-dimensional B from
     # the lifted centers the last step left on the device (trainer.cpp:566)
     ctx.call("isle_cuda_reset_stats")
@@ -413,69 +562,33 @@ def bench_ours(args):
         total_docs = float(D)
 
     if rank == 0:
-        peak, peak_src = load_peaks()
-        spmm_ms = st["spmm_bt_ms"] + st["spmm_b_ms"]
-        spmm_bytes = st["spmm_bt_bytes"] + st["spmm_b_bytes"]
-        ach = spmm_bytes / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
-        ncalls = st["spmm_bt_calls"] + st["spmm_b_calls"]
         h2d = nnz * (4 + 8) + (D + 1) * 8
         d2h = V * 4 + state["DB"] * 8 + k * 4 + k * 8 + 2 * k * k * 4 + V * k * 4
-        line = {
-            "metric": METRIC, "value": total_docs * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config} {SHAPES.get(args.config, 'synthetic')} per GPU: {D} docs x {V} vocab, {nnz} nnz, k={k}",
-                       "block_size": 10, "tol": 1e-4, "l2": "inputs (A: %.0f MB) larger than the 126 MB L2" % (nnz * 8 / 1e6),
-                       "D_B": state["DB"], "nnz_B": state["nnzB"], "ks_restarts": st["ks_restarts"],
-                       "ks_block_steps": st["ks_ops"], "ks_gs_third_passes_elided": st["ks_gs_elided"],
-                       "spmm_head_words": int(st["spmm_head_words"]), "spmm_tail_nnz": int(st["spmm_tail_nnz"]),
-                       "lloyd_iters": state["iters"], "nconv": state["nconv"]},
-            "e2e": {"value": total_docs * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(st["launches"]),
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "B^T X and B Y passes of the operator: spmm_head_kernel (tcgen05 dense head) + "
-                                                         "spmm_gather_bfp_kernel (tail)", "achieved": ach,
-                         "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None, "traffic": load_traffic(args.config),
-                         "peak_source": peak_src, "launches": int(ncalls),
-                         "avg_launch_ms": spmm_ms / ncalls if ncalls else None,
-                         "bytes_per_launch": spmm_bytes / ncalls if ncalls else None},
-            # the one dense contraction of the path (docs x centers distances, Lloyd assignment passes): logical flops
-            # 2 D_B k k per pass; the tensor pipe does 3x that (split TF32: hi*hi + hi*lo + lo*hi)
-            "tensor": (lambda pk: {"kernel": "dist_tc_kernel (tcgen05 kind::tf32, split TF32)", "bound": "tensor",
-                                   "logical_tflops": st["dist_tc_flops"] / (st["dist_tc_ms"] * 1e-3) / 1e12 if st["dist_tc_ms"] else None,
-                                   "pipe_tflops": 3.0 * st["dist_tc_flops"] / (st["dist_tc_ms"] * 1e-3) / 1e12 if st["dist_tc_ms"] else None,
-                                   "peak": pk[0], "unit": "TFLOP/s", "peak_source": pk[1],
-                                   "frac": (3.0 * st["dist_tc_flops"] / (st["dist_tc_ms"] * 1e-3) / 1e12 / pk[0]) if st["dist_tc_ms"] else None})(
-                load_tf32_peak()),
-            "stage_ms_per_step": {n[:-3]: st[n] / args.steps for n in st if n.endswith("_ms")},
-            # block Gram-Schmidt panel products: algorithmic bytes (n x rows x 4 per product) of the passes that ran
-            # (elided third passes return at once and move nothing) / CUDA-event time, reduce kernels included
-            "panel_gbs": (lambda live: {"wtf": live * st["ks_wtf_bytes"] / st["ks_wtf_ms"] / 1e6 if st["ks_wtf_ms"] else None,
-                                        "fsub": live * st["ks_fsub_bytes"] / st["ks_fsub_ms"] / 1e6 if st["ks_fsub_ms"] else None,
-                                        "passes_run_fraction": live})(
-                1.0 - (st["ks_gs_elided"] * args.steps) / max(3.0 * st["ks_ops"], 1.0)),
-            "step_wall_ms": [round(x, 2) for x in step_wall],
-            "next_rows": {"lloyd_full": {"what": "SURVEY 8(f) row 1: run_lloyds on the full-dimensional B (trainer.cpp:566), "
-                                                 "device-resident, not part of the metric", "ms": fms.value, "iters": fit.value,
-                                         "objective": fobj.value, "assign_ms": stf["lloyd_full_assign_ms"],
-                                         "update_ms": stf["lloyd_full_update_ms"],
-                                         "assign_gather_tflops": (stf["lloyd_full_assign_flops"] / (stf["lloyd_full_assign_ms"] * 1e-3) / 1e12
-                                                                  if stf["lloyd_full_assign_ms"] > 0 else None)},
-                          "catchwords": cw},
-            "alloc": {"driver_allocs_in_timed_region": st["alloc_misses"], "cache_hits_per_step": st["alloc_hits"] / args.steps},
-        }
+        if full_dl:
+            d2h += state["nnzB"] * (4 + 8) + (state["DB"] + 1) * 8 + V * k * 4
+        next_rows = {"lloyd_full": {"what": "SURVEY 8(f) row 1: run_lloyds on the full-dimensional B (trainer.cpp:566), "
+                                            "device-resident, not part of the metric", "ms": fms.value, "iters": fit.value,
+                                    "objective": fobj.value, "assign_ms": stf["lloyd_full_assign_ms"],
+                                    "update_ms": stf["lloyd_full_update_ms"],
+                                    "assign_gather_tflops": (stf["lloyd_full_assign_flops"] / (stf["lloyd_full_assign_ms"] * 1e-3) / 1e12
+                                                             if stf["lloyd_full_assign_ms"] > 0 else None)},
+                     "catchwords": cw}
+        line = ours_line(args=args, world=world, cfg_name=args.config, D=D, V=V, nnz=nnz, k=k, sha16=sha16,
+                         total_docs=total_docs, dev_ms=dev_ms, e2e_s=e2e_s, h2d=h2d, d2h=d2h, st=st, state=state,
+                         clocks=clocks, hbm_peak=load_peaks(), tf32_peak=tf32_peak, traffic=load_traffic(args.config),
+                         step_wall=step_wall, next_rows=next_rows)
         if not args.no_cpu_baseline and world == 1:
             try:
                 ncores = os.cpu_count() or 1
-                nd = args.cpu_sample_docs or 30000
-                cs = slice_corpus(c, nd)
+                full = not args.cpu_sample_docs and nnz <= REF_MAX_FULL_NNZ and k <= 500
+                cs = c if full else slice_corpus(c, args.cpu_sample_docs or max(4 * k, 30000))
                 with tempfile.TemporaryDirectory(prefix="isle_ref_") as wd:
                     core_s, wall, meta = run_ref_dump(cs, k, ncores, wd)
                 line["cpu_baseline"] = {
                     "value": cs.D / core_s, "unit": UNIT, "cores": ncores, "kind": "reference",
-                    "sample": f"first {cs.D} docs of the same corpus ({cs.nnz} nnz, V={V}, k={k}), stages A-E in "
-                              f"{core_s:.1f} s; unmodified reference C++ over OpenBLAS + MKL shim (not Intel MKL)",
+                    "sample": (f"{'the identical corpus' if cs.D == D else 'the first ' + str(cs.D) + ' docs of the same corpus'} "
+                               f"({cs.D} docs, {cs.nnz} nnz, V={V}, k={k}), one run of stages A-E in {core_s:.1f} s; unmodified "
+                               f"reference C++ over OpenBLAS + MKL shim (not Intel MKL), ref_dump's own stopwatch"),
                     "stage_s": {x: meta[x] for x in ("t_thresholds", "t_build_B", "t_block_ks", "t_kmeanspp", "t_lloyd")}}
             except Exception as e:  # the baseline is reported, never allowed to sink the bench line
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",

@@ -63,7 +63,9 @@ int isle_cuda_upload_A_u32(isle_cuda_ctx *ctx, uint64_t V, uint64_t D, int64_t n
                            const int64_t *offsets, float avg_doc_sz, uint64_t nz_docs);
 /* Replaces list_word_freqs_by_sorting + compute_thresholds
  * (src/sparseMatrix.cpp:289-333, 357-485).  zetas_out: V floats; *new_nnz_out = number of
- * entries with round(value) >= zeta (the function's return value). */
+ * entries with round(value) >= zeta (the function's return value).  In a sharded context both are
+ * statistics of the WHOLE corpus (the per-word histograms are all-reduced first): *new_nnz_out is the
+ * global count, identical on every rank; the local nnz of B comes from isle_cuda_build_B. */
 int isle_cuda_thresholds(isle_cuda_ctx *ctx, uint64_t k, float *zetas_out,
                          int64_t *new_nnz_out);
 /* Replaces threshold_and_copy (src/sparseMatrix.cpp:1285-1361); with a non-NULL
@@ -97,8 +99,11 @@ int isle_cuda_spsptr_multiply(isle_cuda_ctx *ctx, int b, const float *X_colmajor
 /* Replaces initialize_for_eigensolver + compute_block_ks (src/sparseMatrix.cpp:1150-1158,
  * 1195-1220): restarted block Krylov-Schur, nev=k, ncv=2k+b (block-ks/restarted_block_ks.h).
  * evalues_out: k floats (sigma^2, descending); U_colmajor_out: V*k floats or NULL;
- * *nconv_out = converged pairs.  Returns ISLE_ERR_NOCONV when nconv != k (the reference
- * asserts, src/sparseMatrix.cpp:1207); outputs are still filled. */
+ * *nconv_out = converged pairs.  When max_restarts is exhausted the reference's own rule
+ * (restarted_block_ks.h:302-315, see blockks.cu) sets nconv = k and training carries on with the Ritz
+ * pairs of the last truncation; so does this call, and the counter "ks_unconverged" (isle_cuda_get_stat)
+ * holds the number of pairs whose residual is still above tol.  ISLE_ERR_NOCONV is returned when
+ * nconv != k (the reference asserts, src/sparseMatrix.cpp:1207); outputs are still filled. */
 int isle_cuda_block_ks(isle_cuda_ctx *ctx, uint64_t k, int b, int max_restarts, float tol,
                        uint64_t seed, float *evalues_out, float *U_colmajor_out,
                        int *nconv_out);
@@ -127,6 +132,13 @@ int isle_cuda_lloyd_projected(isle_cuda_ctx *ctx, uint64_t k, float *centers_low
  * argmin_c | ||d||^2 + ||c||^2 - 2 d.c |, first index on ties (cblas_isamin). */
 int isle_cuda_assign_projected(isle_cuda_ctx *ctx, uint64_t k, const float *centers_lowd,
                                uint32_t *assign_out);
+/* Replaces update_min_distsq_to_projected_centers (src/sparseMatrix.cpp:2075-2130) for all documents of B: the
+ * k-means++ refresh for a batch of num_centers new centers (projected_centers: num_centers x k floats, center c at
+ * [c*k, (c+1)*k)):  min_dist[d] = min(min_dist[d], max(||P_d||^2 + ||c||^2 - 2 P_d.c, 0)).  min_dist_inout: D_B
+ * floats.  isle_cuda_kmeanspp runs this internally on device-resident state; the entry point exists so that every
+ * refresh kernel (skinny pass, tcgen05 clamped-min mode, fp32 FMA tiles) can be checked against the oracle. */
+int isle_cuda_update_min_dist(isle_cuda_ctx *ctx, uint64_t num_centers, const float *projected_centers,
+                              float *min_dist_inout);
 /* Replaces left_multiply_by_U_Spectra (src/sparseMatrix.cpp:1438-1450):
  * centers_out (V x ncols, column-major) = U * in (k x ncols column-major, leading dim ld_in).
  * centers_out may be NULL (product computed, result left on the device: device-only timing). */

@@ -65,6 +65,7 @@ SIGNATURES = {
     "isle_cuda_kmeanspp": [_vp, _u64, _u64, _vp, _vp, C.POINTER(_f32)],
     "isle_cuda_lloyd_projected": [_vp, _u64, _vp, _int, _vp, C.POINTER(C.c_double), C.POINTER(_int)],
     "isle_cuda_assign_projected": [_vp, _u64, _vp, _vp],
+    "isle_cuda_update_min_dist": [_vp, _u64, _vp, _vp],
     "isle_cuda_lift_centers": [_vp, _u64, _vp, _u64, _vp],
     "isle_cuda_sample_docs": [_vp, C.c_float, _u64, _vp, C.POINTER(C.c_uint64)],
     "isle_cuda_rth_highest_element": [_vp, _u64, _vp, _u64, _vp],

@@ -72,6 +72,9 @@ CONFIGS = {
     "c4": dict(V=100000, D=11000000, k=2000, mu=4.485, seed=20244),
     # one of the eight document shards of c3 (what each GPU of an 8 x B200 box holds): same V, k, mu
     "c3s": dict(V=141000, D=1025000, k=2000, mu=4.29, seed=20243),
+    # c3-shaped miniature the reference finishes in seconds: k > 256 (several center tiles in the tcgen05 distance
+    # kernel, >= 17 new k-means++ centers per round), ncv = 650 (panel products over more than one K segment)
+    "c3m": dict(V=6000, D=40000, k=320, mu=4.29, seed=20250),
 }
 
 

@@ -314,6 +314,11 @@ int isle_cuda_assign_projected(isle_cuda_ctx *h, uint64_t k, const float *center
     });
 }
 
+int isle_cuda_update_min_dist(isle_cuda_ctx *h, uint64_t num_centers, const float *projected_centers, float *min_dist_inout)
+{
+    return guarded(h, [&](Ctx &c) { update_min_dist(c, num_centers, projected_centers, min_dist_inout); });
+}
+
 int isle_cuda_lift_centers(isle_cuda_ctx *h, uint64_t ncols, const float *in, uint64_t ld_in, float *out)
 {
     return guarded(h, [&](Ctx &c) { lift_centers(c, ncols, in, ld_in, out); });

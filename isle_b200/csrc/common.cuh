@@ -202,7 +202,8 @@ struct Ctx {
     // ---- thresholds
     bool have_zeta = false;
     DevBuf<float> zeta, sqrt_zeta;
-    int64_t new_nnz = 0;                   // local count of kept entries
+    int64_t new_nnz = 0;                   // kept entries over the WHOLE corpus (all ranks: the histogram is all-reduced
+                                           // before the rank rule runs), what the reference's compute_thresholds returns
 
     // ---- B: pattern-only doc-major CSC + word-major CSR copy (values are sqrt_zeta[row])
     bool have_B = false;
@@ -356,6 +357,7 @@ void kmeanspp(Ctx &c, uint64_t k, uint64_t seed, uint64_t *seeds_out, float *cen
 void lloyd_projected(Ctx &c, uint64_t k, float *centers_inout, int max_reps,
                      uint32_t *assign_out, double *objective_out, int *iters_out);
 void assign_projected(Ctx &c, uint64_t k, const float *centers, uint32_t *assign_out);
+void update_min_dist(Ctx &c, uint64_t ncent, const float *centers, float *min_dist_inout);
 void lift_centers(Ctx &c, uint64_t ncols, const float *in, uint64_t ld_in, float *out);
 
 // ---- lloyd_full.cu (run_lloyds on the full-dimensional B)

@@ -501,6 +501,27 @@ void assign_projected(Ctx &c, uint64_t k, const float *centers, uint32_t *assign
     ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }
 
+// update_min_distsq_to_projected_centers (src/sparseMatrix.cpp:2075-2130) over all documents for a batch of
+// `ncent` centers (each of length k, contiguous): min_dist[d] = min(min_dist[d], max(dist(d, c), 0)).
+// The engine is the one k-means++ would pick for a batch of this size (options dist_kernel, dist_tc_min_centers,
+// pp_skinny), so every k-means++ refresh kernel can be checked on its own.
+void update_min_dist(Ctx &c, uint64_t ncent, const float *centers, float *min_dist_inout)
+{
+    ISLE_REQUIRE(c.have_U && c.have_B, ISLE_ERR_ARG, "update_min_dist: needs B and U (run block_ks or set_U)");
+    ISLE_REQUIRE(ncent >= 1 && centers && min_dist_inout, ISLE_ERR_ARG, "update_min_dist: bad arguments");
+    project(c);
+    const uint32_t k = (uint32_t)c.k, kp = (uint32_t)c.kp, DB = (uint32_t)c.DB;
+    DevBuf<float> cc((size_t)ncent * kp), c2(ncent), md(std::max<uint32_t>(DB, 1));
+    ISLE_CUDA_CHECK(cudaMemsetAsync(cc.p, 0, cc.bytes(), c.stream));
+    ISLE_CUDA_CHECK(cudaMemcpy2DAsync(cc.p, (size_t)kp * 4, centers, (size_t)k * 4, (size_t)k * 4, ncent, cudaMemcpyHostToDevice, c.stream));
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(md.p, min_dist_inout, (size_t)DB * 4, cudaMemcpyHostToDevice, c.stream));
+    row_l2_kernel<<<(unsigned)((ncent * 32 + 255) / 256), 256, 0, c.stream>>>(cc.p, (uint32_t)ncent, kp, c2.p);
+    count_launch(c);
+    distance_pass(c, cc.p, c2.p, (uint32_t)ncent, 1, nullptr, md.p);
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(min_dist_inout, md.p, (size_t)DB * 4, cudaMemcpyDeviceToHost, c.stream));
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
 void lloyd_projected(Ctx &c, uint64_t k64, float *centers_inout, int max_reps, uint32_t *assign_out,
                      double *objective_out, int *iters_out)
 {

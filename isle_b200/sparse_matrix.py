@@ -314,6 +314,15 @@ class FPSparseMatrix:
         self.ctx.call("isle_cuda_assign_projected", int(num_centers), ptr(pc), ptr(assign))
         return assign
 
+    def update_min_distsq_to_projected_centers(self, projected_centers: np.ndarray, min_dist: np.ndarray) -> np.ndarray:
+        """src/sparseMatrix.cpp:2075-2130 over all documents: ``projected_centers`` is (num_centers, k), ``min_dist``
+        float32[D_B] is updated in place with min(min_dist, max(dist, 0)) and returned."""
+        pc = np.ascontiguousarray(projected_centers, dtype=np.float32)
+        assert pc.ndim == 2 and pc.shape[1] == self.U_cols
+        assert min_dist.dtype == np.float32 and min_dist.flags["C_CONTIGUOUS"] and min_dist.shape[0] == self._num_docs
+        self.ctx.call("isle_cuda_update_min_dist", pc.shape[0], ptr(pc), ptr(min_dist))
+        return min_dist
+
     def run_lloyds(self, num_centers: int, centers: np.ndarray, closest_docs: Optional[List[list]] = None,
                    max_reps: int = MAX_KMEANS_REPS) -> float:
         """src/sparseMatrix.cpp:1679-1746: Lloyd's on the full-dimensional B.

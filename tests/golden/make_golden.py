@@ -105,7 +105,20 @@ def main_stage_g():
     for name in ("tiny", "c1"):
         np.savez_compressed(os.path.join(here, f"{name}_stageG.npz"), **stage_g(name))
 
+def main_c3m():
+    """c3-shaped miniature at k = 320 (corpus.CONFIGS['c3m']): the large-k kernel modes (several center tiles and the
+    clamped-min mode of the tcgen05 distance kernel, panel products over several K segments, Gram-Schmidt pass elision at
+    ncv = 650, eig_sym of a 640 x 640 projected matrix) pinned to the reference's own output.  U is stored in full
+    (V x k fp32): the Lloyd parity test installs exactly the projection the reference used."""
+    here = os.path.dirname(__file__)
+    c, tmp, out, ld = run("c3m")
+    np.savez_compressed(os.path.join(here, "c3m.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--c3m" in sys.argv:
+        main_c3m()
+        sys.exit(0)
     if "--stage-f" in sys.argv:      # adds the stage-F fixtures without touching the stage A-E ones
         main_stage_f()
         sys.exit(0)
@@ -142,3 +155,4 @@ if __name__ == "__main__":
     main_stage_f()
     main_stage_g()
     main_stage_h()
+    main_c3m()

@@ -86,6 +86,11 @@ def main():
             print(f"[rank {rank}] FAIL: {msg}", flush=True)
 
     check(np.array_equal(r["z"], s["z"]), "thresholds differ from the single-GPU run")
+    # compute_thresholds returns the kept-entry count of the WHOLE corpus on every rank (include/isle_cuda.h)
+    check(r["nn"] == s["nn"], f"kept-entry count {r['nn']} differs from the single-GPU run's {s['nn']}")
+    tot = torch.tensor([len(r["bv"])], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot)
+    check(int(tot.item()) == s["nn"], "local nnz of B do not add up to the global kept-entry count")
     # my slice of the single-GPU B: original docs [d0, d1)
     sel = np.nonzero((s["oc"] >= d0) & (s["oc"] < d1))[0]
     check(len(sel) == len(r["oc"]) and np.array_equal(s["oc"][sel] - d0, r["oc"]), "original_cols differ")

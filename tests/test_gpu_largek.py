@@ -1,0 +1,304 @@
+"""Large-k parity (-m gpu): the kernel modes only the k = 2000 path of the north star takes, pinned to the
+reference's own output on a c3-shaped miniature (tests/golden/c3m.npz: 40k docs x 6k vocab, k = 320, made by
+tests/golden/make_golden.py --c3m from the unmodified reference):
+
+  * block Krylov-Schur at ncv = 650: tcgen05 panel products over several K segments, third Gram-Schmidt pass elided on
+    the device and not elided, eig_sym of a 640 x 640 projected matrix (block-ks/restarted_block_ks.h:63-187)
+  * Lloyd from the reference's (U, C0) with 320 centers: dist_tc_kernel with two center tiles (running arg-min
+    across tiles) and ten K blocks (src/sparseMatrix.cpp:1852-1871, 1921-2013)
+  * the k-means++ refresh (src/sparseMatrix.cpp:2075-2130) for batches of 1 ... 320 new centers through every engine:
+    skinny pass, tcgen05 clamped-min mode, fp32 FMA tiles -- against the oracle's distance matrix
+  * the panel engines at rows >= 2048 (several 512-wide K segments of F -= W C) against float64
+  * the distance engines against each other and against an fp64 arg-min on shapes with 1-3 center tiles
+  * the operator's engines on a c2-sized corpus (formerly tools/spmm_check.py)
+Every call goes through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import isle_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def golden_c3m():
+    return dict(np.load(os.path.join(GOLDEN, "c3m.npz")))
+
+
+@pytest.fixture(scope="module")
+def c3m_host(golden_c3m):
+    """The c3m corpus, the oracle's B and the reference's projection (host side, computed once)."""
+    from isle_b200 import corpus
+    from test_gpu_parity import sha
+    g = golden_c3m
+    c = corpus.generate("c3m")
+    assert sha(c.offsets, c.rows, c.counts) == str(g["corpus_sha"])
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    bv, br, bo, boc = O.threshold_and_copy(vals, c.rows, c.offsets, g["zetas"])
+    Bo = O.to_csc(bv, br, bo, c.V)
+    U_ref = g["U_colmajor"].reshape(c.k, c.V).T.copy()
+    P_ref = O.project(Bo, U_ref)
+    return dict(c=c, vals=vals, avg=avg, nz=nz, Bo=Bo, U_ref=U_ref, P_ref=P_ref, d2=O.docs_l2sq(P_ref))
+
+
+@pytest.fixture
+def c3m(ctx, c3m_host):
+    """A and B of c3m on the device (the context holds one corpus at a time, so every test uploads its own)."""
+    from isle_b200.sparse_matrix import FPSparseMatrix, SparseMatrix
+    s = dict(c3m_host)
+    c = s["c"]
+    A = SparseMatrix(c.V, c.D, ctx)
+    A.populate_normalized(s["vals"], c.rows, c.offsets, s["avg"], s["nz"])
+    zetas, nn = A.compute_thresholds(0, c.V, A.list_word_freqs_by_sorting(), c.k)
+    B = FPSparseMatrix(A)
+    oc = B.threshold_and_copy(A, zetas, nn)
+    s.update(A=A, B=B, zetas=zetas, nn=nn, oc=oc)
+    return s
+
+
+def test_c3m_thresholds_and_B_bit_exact(ctx, golden_c3m, c3m):
+    from test_gpu_parity import sha
+    g, s = golden_c3m, c3m
+    assert np.array_equal(s["zetas"], g["zetas"]) and s["nn"] == int(g["new_nnzs"])
+    bv, br, bo, boc = s["B"].download()
+    assert sha(bv, br.astype(np.uint32), bo, boc.astype(np.uint32)) == str(g["B_sha"])
+    assert s["B"].num_docs() == int(g["D_B"]) and s["B"].get_nnzs() == int(g["nnz_B"])
+
+
+@pytest.mark.parametrize("elide", [1, 0], ids=["gs-elision", "three-passes"])
+def test_c3m_block_ks_matches_reference(ctx, golden_c3m, c3m, elide):
+    """sigma within 1e-4 relative, principal angle < 1e-3 against the reference's evalues / U at k = 320, ncv = 650."""
+    from test_gpu_parity import check_eigs
+    g, s = golden_c3m, c3m
+    c, B = s["c"], s["B"]
+    try:
+        ctx.set_option("ks_gs_elide", elide)
+        ev, U = B.compute_block_ks(c.k, seed=5, want_U=True)
+        elided = ctx.stat("ks_gs_elided")
+    finally:
+        ctx.set_option("ks_gs_elide", 1)
+    assert B.nconv == c.k
+    assert (elided > 0) == bool(elide)
+    check_eigs(ev, U, g["evalues"], s["U_ref"], float(g["frobenius"]))
+    # Ritz residuals through the operator for the first, middle and last block
+    for j0 in (0, c.k // 2, c.k - 10):
+        Uj = np.ascontiguousarray(U[:, j0:j0 + 10])
+        R = B.multiply(Uj).astype(np.float64) - Uj.astype(np.float64) * ev[j0:j0 + 10].astype(np.float64)
+        assert np.max(np.linalg.norm(R, axis=0) / ev[j0:j0 + 10]) < 5e-4
+
+
+@pytest.mark.parametrize("engine", [1, 0], ids=["tcgen05", "fma"])
+def test_c3m_assignment_and_lloyd_match_reference(ctx, golden_c3m, c3m, engine):
+    """Identical projection and initial centers as the reference (set_U, centers_lowd_init): one assignment pass against
+    the oracle's fp32 distance matrix, then Lloyd's to the reference's stopping rule against its final partition."""
+    g, s = golden_c3m, c3m
+    c, B = s["c"], s["B"]
+    k = c.k
+    try:
+        ctx.set_option("dist_kernel", engine)
+        B.set_U(s["U_ref"])
+        P, l2 = B.projected_docs()
+        assert np.max(np.abs(P - s["P_ref"])) <= 1e-5 * np.max(np.abs(s["P_ref"]))
+        C0 = np.ascontiguousarray(g["centers_lowd_init"].reshape(k, k))
+        a = B.projected_closest_centers(k, C0)
+        dm = np.abs(O.dist_matrix(s["P_ref"], s["d2"], C0))
+        a_ref = dm.argmin(1)
+        diff = np.nonzero(a != a_ref)[0]
+        # any difference must be a genuine near-tie of the two candidates (relative to ||d||^2: the cancellation scale)
+        gap = np.abs(dm[diff, a[diff].astype(np.int64)] - dm[diff, a_ref[diff]]) / np.maximum(s["d2"][diff], 1e-30)
+        assert len(diff) <= 4 and (len(diff) == 0 or gap.max() < 1e-5), (len(diff), gap)
+        assert int(ctx.stat("dist_tc_calls" if engine else "dist_simt_calls")) > 0
+        C = C0.copy()
+        B.run_lloyds_on_projected_space(k, C, None, 10)
+        mism = int((B.last_lloyd["assign"] != g["lloyd_assign"]).sum())
+        assert mism <= 8, mism                                    # ties excepted (40k docs, 320 centers, 10 iterations)
+        Cr = g["centers_lowd_final"].reshape(k, k)
+        assert np.max(np.abs(C - Cr)) <= 1e-3 * np.max(np.abs(Cr))
+        obj_ref = O.kmeans_objective(s["P_ref"], Cr, g["lloyd_assign"])
+        assert abs(B.last_lloyd["objective"] - obj_ref) / obj_ref < 1e-4
+    finally:
+        ctx.set_option("dist_kernel", 1)
+
+
+# engine selection of the k-means++ refresh (kmeans.cu distance_pass): options forcing each kernel
+PP_ENGINES = {
+    "skinny": dict(dist_kernel=1, pp_skinny=1, dist_tc_min_centers=17),          # <= 16 centers: one pass over P
+    "tcgen05": dict(dist_kernel=1, pp_skinny=1, dist_tc_min_centers=1),           # clamped-min mode of dist_tc_kernel
+    "fma": dict(dist_kernel=0, pp_skinny=0, dist_tc_min_centers=17),              # fp32 FMA tiles
+}
+PP_DEFAULTS = dict(dist_kernel=1, pp_skinny=1, dist_tc_min_centers=17)
+
+
+@pytest.mark.parametrize("ncent", [1, 5, 16, 17, 40, 300])
+@pytest.mark.parametrize("engine", list(PP_ENGINES))
+def test_c3m_min_dist_update_matches_oracle(ctx, golden_c3m, c3m, engine, ncent):
+    """update_min_distsq_to_projected_centers (src/sparseMatrix.cpp:2075-2130) for a fixed batch of new centers:
+    min(min_dist, max(dist, 0)) against the oracle's fp32 distance matrix.  Distances are formed by cancellation
+    (||d||^2 + ||c||^2 - 2 d.c), so the tolerance is relative to ||d||^2 + ||c||^2."""
+    g, s = golden_c3m, c3m
+    c, B = s["c"], s["B"]
+    if engine == "skinny" and ncent > 16:
+        pytest.skip("the skinny pass handles at most 16 centers per launch")
+    rng = np.random.default_rng(100 + ncent)
+    P_ref, d2 = s["P_ref"], s["d2"]
+    ids = rng.choice(len(P_ref), ncent, replace=False)
+    Cn = np.ascontiguousarray(P_ref[ids] + (0.0 if ncent == 5 else 1e-3) * rng.standard_normal((ncent, c.k)).astype(np.float32))
+    md0 = (np.abs(rng.standard_normal(len(P_ref))) * np.median(d2)).astype(np.float32)
+    md0[::3] = np.float32(3.4e38)                                  # FLT_MAX-like: the state before the first refresh (:2149)
+    try:
+        for k_, v_ in PP_ENGINES[engine].items():
+            ctx.set_option(k_, v_)
+        B.set_U(s["U_ref"])
+        ctx.call("isle_cuda_reset_stats")
+        md = B.update_min_distsq_to_projected_centers(Cn, md0.copy())
+        used = {n: ctx.stat(n + "_calls") for n in ("pp_dist_skinny", "pp_dist_tc", "pp_dist_simt")}
+    finally:
+        for k_, v_ in PP_DEFAULTS.items():
+            ctx.set_option(k_, v_)
+    assert used[{"skinny": "pp_dist_skinny", "tcgen05": "pp_dist_tc", "fma": "pp_dist_simt"}[engine]] == 1, used
+    dm = np.maximum(O.dist_matrix(P_ref, d2, Cn), 0.0)
+    ref = np.minimum(md0, dm.min(1))
+    scale = d2 + (Cn.astype(np.float64) ** 2).sum(1).max()
+    assert np.max(np.abs(md - ref) / scale) < 2e-6
+    assert np.all(md >= 0) and np.all(md <= md0)
+    if ncent == 5:                                                 # documents that ARE a center end at distance ~0 (:2175)
+        assert np.all(md[ids] <= 2e-6 * scale[ids])
+
+
+@pytest.mark.parametrize("shape", [(4000, 1500, 40), (30000, 3000, 160), (40000, 4000, 520)],
+                         ids=["1-tile", "1-tile-k160", "3-tiles-k520"])
+def test_distance_engines_agree(ctx, shape):
+    """tcgen05 split-TF32 engine vs the fp32 FMA engine vs an fp64 arg-min (formerly tools/dist_tc_check.py): the
+    engines may only differ on genuine near-ties, and the tensor-core engine is as close to fp64 as the FMA one."""
+    from isle_b200 import corpus
+    from isle_b200.sparse_matrix import FPSparseMatrix, SparseMatrix
+    D, V, k = shape
+    rng = np.random.default_rng(D + V + k)
+    c = corpus.generate(V=V, D=D, k=max(4, min(k, 50)), mu=4.0, seed=7)
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    A = SparseMatrix(V, D, ctx)
+    A.populate_normalized(vals, c.rows, c.offsets, avg, nz)
+    z, nn = A.compute_thresholds(0, V, None, max(2, min(k, 50)))
+    B = FPSparseMatrix(A)
+    B.threshold_and_copy(A, z, nn)
+    U, _ = np.linalg.qr(rng.standard_normal((V, k)))
+    out = {}
+    try:
+        for eng in (1, 0):
+            ctx.set_option("dist_kernel", eng)
+            B.set_U(U.astype(np.float32))
+            if eng == 1:
+                P, l2 = B.projected_docs()
+                DB = P.shape[0]
+                C = np.ascontiguousarray(P[rng.choice(DB, k, replace=False)] + 0.01 * rng.standard_normal((k, k)).astype(np.float32))
+            out[eng] = B.projected_closest_centers(k, C)
+    finally:
+        ctx.set_option("dist_kernel", 1)
+    a0, a1 = out[0], out[1]
+    P64, C64 = P.astype(np.float64), C.astype(np.float64)
+    d64 = np.abs((P64 ** 2).sum(1)[:, None] + (C64 ** 2).sum(1)[None, :] - 2.0 * P64 @ C64.T)
+    ref = d64.argmin(1)
+    diff = np.nonzero(a0 != a1)[0]
+    gap = np.abs(d64[diff, a0[diff].astype(np.int64)] - d64[diff, a1[diff].astype(np.int64)]) / np.maximum((P64[diff] ** 2).sum(1), 1e-30)
+    assert len(diff) == 0 or gap.max() < 1e-5, (len(diff), gap.max())
+    m0, m1 = int((ref != a0).sum()), int((ref != a1).sum())
+    assert m1 <= max(5, 2 * m0 + 5), (m0, m1)
+
+
+@pytest.mark.parametrize("engine", [0, 2], ids=["fma-scalar", "tcgen05"])
+@pytest.mark.parametrize("shape", [(8192, 2304, 10), (6000, 4010, 10), (12288, 2050, 16)])
+def test_panel_products_many_k_segments(ctx, engine, shape):
+    """C = W^T F and F -= W C (restarted_block_ks.h:83-84) with rows >= 2048: F -= W C runs over >= 5 K segments of 512
+    columns in the tensor-core engine (4010 = ncv of the k = 2000 target), W^T F over >= 12."""
+    from isle_b200._capi import ptr
+    n, rows, b = shape
+    rng = np.random.default_rng(n + rows + b)
+    W = (rng.standard_normal((rows, n)) / np.sqrt(n)).astype(np.float32)          # C-order rows x n == column-major n x rows
+    F = (rng.standard_normal((b, n)) * np.logspace(0, -3, b)[:, None]).astype(np.float32)
+    Fc, Cc = F.copy(), np.zeros((b, rows), np.float32)
+    ctx.call("isle_cuda_panel_products", n, rows, b, ptr(W), ptr(Fc), ptr(Cc), engine)
+    W64, F64 = W.astype(np.float64), F.astype(np.float64)
+    fn = np.linalg.norm(F64, axis=1)
+    C_ref = F64 @ W64.T                                                            # b x rows
+    assert np.max(np.abs(Cc - C_ref) / fn[:, None]) < 2e-6
+    F_ref = F64 - Cc.astype(np.float64) @ W64
+    # F -= W C sums `rows` products per entry: error relative to the magnitudes summed
+    mag = np.abs(Cc.astype(np.float64)) @ np.abs(W64) + np.abs(F64)
+    assert np.max(np.abs(Fc - F_ref) / np.maximum(mag, 1e-30)) < 2e-6
+
+
+def test_operator_engines_at_c2_size(ctx):
+    """The operator through every engine combination on a 100k-document slice of the c2 shape (formerly
+    tools/spmm_check.py): head on tcgen05 + block-FP tail vs index lists only, against a float64 product."""
+    import scipy.sparse as sp
+    import torch
+
+    from isle_b200 import corpus
+    from isle_b200.sparse_matrix import FPSparseMatrix, SparseMatrix
+    cfg = corpus.CONFIGS["c2"]
+    c = corpus.generate(V=cfg["V"], D=100000, k=cfg["k"], mu=cfg["mu"], seed=cfg["seed"], backend="torch", device="cuda:0")
+    torch.cuda.empty_cache()
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    A = SparseMatrix(c.V, c.D, ctx)
+    A.populate_normalized(vals, c.rows, c.offsets, avg, nz)
+    zetas, nn = A.compute_thresholds(0, c.V, None, c.k)
+    B = FPSparseMatrix(A)
+    B.threshold_and_copy(A, zetas, nn)
+    bv, br, bo, _ = B.download()
+    Bm = sp.csc_matrix((bv.astype(np.float64), br.astype(np.int64), bo), shape=(c.V, B.num_docs()))
+    X = np.random.default_rng(1).standard_normal((c.V, 10)).astype(np.float32)
+    Zr = Bm @ (Bm.T @ X.astype(np.float64))
+    scale = np.max(np.abs(Zr), axis=0)
+    defaults = dict(spmm_head=1, spmm_bfp=1, spmm_fork=1, spmm_head_density_ppm=12000)
+    try:
+        for opts in (dict(spmm_head=0, spmm_bfp=0), dict(spmm_head=0), dict(spmm_fork=0), dict(), dict(spmm_head_density_ppm=4000)):
+            for k_, v_ in {**defaults, **opts}.items():
+                ctx.set_option(k_, v_)
+            Z = B.multiply(X)
+            H = int(ctx.stat("spmm_head_words"))
+            assert (H > 0) == bool({**defaults, **opts}["spmm_head"])
+            assert np.max(np.abs(Z - Zr) / scale) <= 3e-6, opts
+    finally:
+        for k_, v_ in defaults.items():
+            ctx.set_option(k_, v_)
+
+
+def test_c2_size_masked_build_bit_exact(ctx):
+    """The c4 path (sampled_threshold_and_copy, src/sparseMatrix.cpp:1365-1435) at c2 size with a harness mask of
+    rate 0.1: weights, B and original_cols bit-exact against the numpy oracle."""
+    import torch
+
+    from isle_b200 import corpus
+    from isle_b200._capi import ptr
+    from isle_b200.sparse_matrix import FPSparseMatrix, SparseMatrix
+    cfg = corpus.CONFIGS["c2"]
+    c = corpus.generate(V=cfg["V"], D=cfg["D"], k=cfg["k"], mu=cfg["mu"], seed=cfg["seed"] + 4, backend="torch", device="cuda:0")
+    torch.cuda.empty_cache()
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    A = SparseMatrix(c.V, c.D, ctx)
+    A.populate_normalized(vals, c.rows, c.offsets, avg, nz)
+    zetas, nn = A.compute_thresholds(0, c.V, None, c.k)
+    z_ref, nn_ref = O.compute_thresholds(vals, c.rows, c.V, nz, c.k)
+    assert np.array_equal(zetas, z_ref) and nn == nn_ref
+    w = np.zeros(c.D, np.float32)
+    ctx.call("isle_cuda_sampling_weights", ptr(w))
+    assert np.array_equal(w.view(np.uint32), O.sampling_weights(vals, c.rows, c.offsets, z_ref).view(np.uint32))
+    # A-Res selection with harness uniforms (the reference's rand() is racy; the mask is injected on both sides)
+    u = np.random.default_rng(3).random(c.D)
+    with np.errstate(divide="ignore"):
+        key = np.where(w == 0, 0.0, np.power(u, 1.0 / np.maximum(w, 1e-30))).astype(np.float32)
+    nth = int(np.float32(0.1) * np.float32(c.D))
+    pivot = np.sort(key)[::-1][nth]
+    mask = (key >= pivot).astype(np.uint8)
+    B = FPSparseMatrix(A)
+    oc = B.sampled_threshold_and_copy(A, zetas, nn, 0.1, select_docs=mask)
+    bv, br, bo, boc = O.threshold_and_copy(vals, c.rows, c.offsets, z_ref, select_docs=mask.astype(bool))
+    gv, gr, go, goc = B.download()
+    assert B.num_docs() == len(boc) and abs(B.num_docs() - (nth + 1)) <= 2
+    assert np.array_equal(go, bo) and np.array_equal(gr, br.astype(np.uint64))
+    assert np.array_equal(gv.view(np.uint32), bv.view(np.uint32))
+    assert np.array_equal(goc, boc.astype(np.uint64)) and np.array_equal(oc, goc)
