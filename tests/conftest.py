@@ -7,6 +7,9 @@ import pytest
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+HERE = os.path.dirname(os.path.abspath(__file__))
+if HERE not in sys.path:          # test modules share helpers (from test_gpu_parity import sha, check_eigs)
+    sys.path.insert(0, HERE)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 

@@ -42,7 +42,14 @@ def c3m_host(golden_c3m):
     Bo = O.to_csc(bv, br, bo, c.V)
     U_ref = g["U_colmajor"].reshape(c.k, c.V).T.copy()
     P_ref = O.project(Bo, U_ref)
-    return dict(c=c, vals=vals, avg=avg, nz=nz, Bo=Bo, U_ref=U_ref, P_ref=P_ref, d2=O.docs_l2sq(P_ref))
+    # the exact invariant subspace (fp64 eigh of the 6000 x 6000 Gram matrix, seconds): the reference's own U is only
+    # tol / gap accurate -- at c3m the k-th eigenvalue is 0.46 % above the next one and the reference's subspace is
+    # 1.4e-3 (sin of the largest principal angle) away from the exact one
+    B64 = Bo.astype(np.float64)
+    w, Q = np.linalg.eigh((B64 @ B64.T).toarray())
+    U_exact, ev_exact = Q[:, ::-1][:, :c.k].copy(), w[::-1][:c.k + 1].copy()
+    return dict(c=c, vals=vals, avg=avg, nz=nz, Bo=Bo, U_ref=U_ref, P_ref=P_ref, d2=O.docs_l2sq(P_ref),
+                U_exact=U_exact, ev_exact=ev_exact, ang_ref_exact=O.principal_angle_sin(U_ref, U_exact))
 
 
 @pytest.fixture
@@ -69,57 +76,97 @@ def test_c3m_thresholds_and_B_bit_exact(ctx, golden_c3m, c3m):
     assert s["B"].num_docs() == int(g["D_B"]) and s["B"].get_nnzs() == int(g["nnz_B"])
 
 
+def _span_residual(X, U):
+    """largest singular value of (I - U U^T) X: how far the columns of X stick out of span(U)"""
+    X, U = X.astype(np.float64), U.astype(np.float64)
+    return float(np.linalg.norm(X - U @ (U.T @ X), 2))
+
+
 @pytest.mark.parametrize("elide", [1, 0], ids=["gs-elision", "three-passes"])
 def test_c3m_block_ks_matches_reference(ctx, golden_c3m, c3m, elide):
-    """sigma within 1e-4 relative, principal angle < 1e-3 against the reference's evalues / U at k = 320, ncv = 650."""
-    from test_gpu_parity import check_eigs
+    """k = 320, ncv = 650 against the reference's evalues / U.  Singular values within 1e-4 relative.  The subspace: the
+    k-th eigenvalue of c3m sits 0.46 % above the (k+1)-th, so a solver that stops at residual 1e-4 (the reference's rule,
+    restarted_block_ks.h:276-293) pins span(U) only to ~tol / gap: the reference's own U is 1.4e-3 away from the exact
+    subspace (fixture).  The bars are therefore: our subspace at least as close to the exact one as the reference's is;
+    the angle between the two solvers within the sum of their distances to the exact subspace (and < 1e-3 wherever both
+    are that accurate); the well-separated leading 300 Ritz vectors inside the other solver's span to 1e-3."""
     g, s = golden_c3m, c3m
     c, B = s["c"], s["B"]
+    k = c.k
     try:
         ctx.set_option("ks_gs_elide", elide)
-        ev, U = B.compute_block_ks(c.k, seed=5, want_U=True)
+        ev, U = B.compute_block_ks(k, seed=5, want_U=True)
         elided = ctx.stat("ks_gs_elided")
     finally:
         ctx.set_option("ks_gs_elide", 1)
-    assert B.nconv == c.k
+    assert B.nconv == k
     assert (elided > 0) == bool(elide)
-    check_eigs(ev, U, g["evalues"], s["U_ref"], float(g["frobenius"]))
+    sv, sv_ref, sv_exact = np.sqrt(ev), np.sqrt(g["evalues"]), np.sqrt(s["ev_exact"][:k])
+    assert np.all(np.diff(ev) <= 1e-3 * ev[:-1])
+    assert np.max(np.abs(sv - sv_ref) / sv_ref) < 1e-4
+    assert np.max(np.abs(sv - sv_exact) / sv_exact) < 1e-4
+    assert np.linalg.norm(U.T.astype(np.float64) @ U - np.eye(k)) < 1e-4
+    assert ev.sum() <= float(g["frobenius"]) * (1 + 1e-6)
+    ang_ours, ang_ref = O.principal_angle_sin(U, s["U_exact"]), s["ang_ref_exact"]
+    ang_both = O.principal_angle_sin(U, s["U_ref"])
+    print(f"c3m subspace: ours vs exact {ang_ours:.3e}, reference vs exact {ang_ref:.3e}, ours vs reference {ang_both:.3e}")
+    assert ang_ours <= max(1e-3, 1.25 * ang_ref), (ang_ours, ang_ref)
+    assert ang_both <= max(1e-3, 1.05 * (ang_ours + ang_ref)), (ang_both, ang_ours, ang_ref)
+    assert _span_residual(U[:, :300], s["U_ref"]) < 1e-3 and _span_residual(s["U_ref"][:, :300], U) < 1e-3
     # Ritz residuals through the operator for the first, middle and last block
-    for j0 in (0, c.k // 2, c.k - 10):
+    for j0 in (0, k // 2, k - 10):
         Uj = np.ascontiguousarray(U[:, j0:j0 + 10])
         R = B.multiply(Uj).astype(np.float64) - Uj.astype(np.float64) * ev[j0:j0 + 10].astype(np.float64)
         assert np.max(np.linalg.norm(R, axis=0) / ev[j0:j0 + 10]) < 5e-4
 
 
+def _near_tie_only(dm, d2, a, a_ref, max_diff):
+    """assignments may differ from the oracle's only on genuine near-ties of the two candidates (gap relative to
+    ||d||^2, the scale the distances are formed at by cancellation)"""
+    diff = np.nonzero(a != a_ref)[0]
+    gap = np.abs(dm[diff, a[diff].astype(np.int64)] - dm[diff, a_ref[diff]]) / np.maximum(d2[diff], 1e-30)
+    assert len(diff) <= max_diff and (len(diff) == 0 or gap.max() < 1e-5), (len(diff), gap)
+
+
 @pytest.mark.parametrize("engine", [1, 0], ids=["tcgen05", "fma"])
 def test_c3m_assignment_and_lloyd_match_reference(ctx, golden_c3m, c3m, engine):
-    """Identical projection and initial centers as the reference (set_U, centers_lowd_init): one assignment pass against
-    the oracle's fp32 distance matrix, then Lloyd's to the reference's stopping rule against its final partition."""
+    """Identical projection and initial centers as the reference (set_U, centers_lowd_init), 320 centers = two center
+    tiles of the tcgen05 kernel.  (i) Ten assignment passes along the ORACLE's Lloyd trajectory (both sides see the same
+    centers at every iteration): identical partitions, near-ties excepted.  (ii) One Lloyd iteration: centers = member
+    means within 1e-5.  (iii) Ten free-running iterations against the reference's output: k-means objective within 1e-4;
+    the partitions themselves drift apart through tie flips (the numpy oracle, another fp32 summation order of the same
+    algorithm, ends 267 documents = 0.7 % away from the reference as well)."""
     g, s = golden_c3m, c3m
     c, B = s["c"], s["B"]
     k = c.k
+    P_ref, d2 = s["P_ref"], s["d2"]
     try:
         ctx.set_option("dist_kernel", engine)
         B.set_U(s["U_ref"])
         P, l2 = B.projected_docs()
-        assert np.max(np.abs(P - s["P_ref"])) <= 1e-5 * np.max(np.abs(s["P_ref"]))
+        assert np.max(np.abs(P - P_ref)) <= 1e-5 * np.max(np.abs(P_ref))
         C0 = np.ascontiguousarray(g["centers_lowd_init"].reshape(k, k))
-        a = B.projected_closest_centers(k, C0)
-        dm = np.abs(O.dist_matrix(s["P_ref"], s["d2"], C0))
-        a_ref = dm.argmin(1)
-        diff = np.nonzero(a != a_ref)[0]
-        # any difference must be a genuine near-tie of the two candidates (relative to ||d||^2: the cancellation scale)
-        gap = np.abs(dm[diff, a[diff].astype(np.int64)] - dm[diff, a_ref[diff]]) / np.maximum(s["d2"][diff], 1e-30)
-        assert len(diff) <= 4 and (len(diff) == 0 or gap.max() < 1e-5), (len(diff), gap)
-        assert int(ctx.stat("dist_tc_calls" if engine else "dist_simt_calls")) > 0
+        Ci = C0.copy()
+        for it in range(10):
+            a = B.projected_closest_centers(k, Ci)
+            dm = np.abs(O.dist_matrix(P_ref, d2, Ci))
+            _near_tie_only(dm, d2, a, dm.argmin(1), 6)
+            Ci, _ = O.lloyds_iter(P_ref, d2, Ci)
+            Ci = np.ascontiguousarray(Ci, dtype=np.float32)
+        assert int(ctx.stat("dist_tc_calls" if engine else "dist_simt_calls")) >= 10
+        C1 = C0.copy()
+        B.run_lloyds_on_projected_space(k, C1, None, 1)
+        C1_ref, a1_ref = O.lloyds_iter(P_ref, d2, C0)
+        assert int((B.last_lloyd["assign"] != a1_ref).sum()) <= 6
+        assert np.max(np.abs(C1 - C1_ref)) <= 2e-3 * np.max(np.abs(C1_ref))      # a flipped near-tie moves two means by 1/|cluster|
+        assert np.median(np.abs(C1 - C1_ref).max(1)) <= 1e-5 * np.max(np.abs(C1_ref))
         C = C0.copy()
         B.run_lloyds_on_projected_space(k, C, None, 10)
-        mism = int((B.last_lloyd["assign"] != g["lloyd_assign"]).sum())
-        assert mism <= 8, mism                                    # ties excepted (40k docs, 320 centers, 10 iterations)
         Cr = g["centers_lowd_final"].reshape(k, k)
-        assert np.max(np.abs(C - Cr)) <= 1e-3 * np.max(np.abs(Cr))
-        obj_ref = O.kmeans_objective(s["P_ref"], Cr, g["lloyd_assign"])
+        obj_ref = O.kmeans_objective(P_ref, Cr, g["lloyd_assign"])
         assert abs(B.last_lloyd["objective"] - obj_ref) / obj_ref < 1e-4
+        assert abs(O.kmeans_objective(P_ref, C, B.last_lloyd["assign"]) - B.last_lloyd["objective"]) / obj_ref < 1e-5
+        assert np.mean(B.last_lloyd["assign"] != g["lloyd_assign"]) < 0.02
     finally:
         ctx.set_option("dist_kernel", 1)
 
@@ -163,10 +210,13 @@ def test_c3m_min_dist_update_matches_oracle(ctx, golden_c3m, c3m, engine, ncent)
     dm = np.maximum(O.dist_matrix(P_ref, d2, Cn), 0.0)
     ref = np.minimum(md0, dm.min(1))
     scale = d2 + (Cn.astype(np.float64) ** 2).sum(1).max()
-    assert np.max(np.abs(md - ref) / scale) < 2e-6
+    # the fp32 FMA engines round to nearest; the tensor core adds into its fp32 TMEM accumulator by truncation, so the
+    # 3 k / 8 = 120 accumulations of a k = 320 dot product leave a one-sided error of up to ~120 x 2^-24 of |P_d . c|
+    tol = 1e-5 if engine == "tcgen05" else 2e-6
+    assert np.max(np.abs(md - ref) / scale) < tol
     assert np.all(md >= 0) and np.all(md <= md0)
     if ncent == 5:                                                 # documents that ARE a center end at distance ~0 (:2175)
-        assert np.all(md[ids] <= 2e-6 * scale[ids])
+        assert np.all(md[ids] <= tol * scale[ids])
 
 
 @pytest.mark.parametrize("shape", [(4000, 1500, 40), (30000, 3000, 160), (40000, 4000, 520)],
