@@ -1016,7 +1016,7 @@ void block_ks(Ctx &c, uint64_t k64, int b, int max_restarts, float tol, uint64_t
                  "block_ks: k must be a multiple of the block size (reference expand() writes V out of "
                  "bounds otherwise, restarted_block_ks.h:71-100)");
     ISLE_REQUIRE((uint64_t)(2 * k + b) <= c.V, ISLE_ERR_ARG, "block_ks: ncv = 2k+b exceeds the vocabulary size");
-    build_csr(c);
+    build_csr(c, b <= 10 && c.opt("spmm_bfp", 1) != 0);
     KsState ks(c, k, b, seed);
     ks.init();
     int nconv = 0, n_restarts = 0;

@@ -234,6 +234,9 @@ struct Ctx {
     DevBuf<uint4> xbfp, ybfp;              // one-sector (32-byte) copies of the operand rows, two 16-byte units per row
     DevBuf<uint4> bits1, bits2;            // head bitmaps: (doc tile x rank chunk) and (rank tile x doc chunk)
     DevBuf<__nv_bfloat16> xsplit, ysplit;  // 3-piece bf16 splits of the head rows of Xs / of Y, K-major [N][Kpad]
+    bool head_i8 = false;                  // layout built for the int8 head engine (spmm_head_i8.cu): 256-k super-chunks, plane-major bits
+    DevBuf<int8_t> xdig, ydig;             // three s8 digits of the quantised head rows of Xs / of Y, K-major [32][Kpad]
+    DevBuf<uint32_t> ycolmax;              // per-column max |Y| (bit patterns): quantisation scale of pass 2
     uint32_t *head_diag_host = nullptr, *head_diag_dev = nullptr;   // host-mapped timeout record of the head kernel
     cudaStream_t stream2 = nullptr;        // head pass 2 runs beside the tail pass 2
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -294,6 +297,29 @@ struct StatScope {
 
 inline void count_launch(Ctx &c, int n = 1) { c.launches += n; }
 
+// Quantisation of a dense operand column for the int8 head engine (spmm_head_i8.cu): q = rn(x * 2^(21 - e)) with
+// 2^e <= column max < 2^(e+1), so |q| < 2^22 fits three balanced base-256 digits; the value is q * 2^(e - 21).
+// `colmax_bits` = bit pattern of the column's max |x| (NULL / 0 / non-finite: e = 0).  Returns the biased exponent.
+__device__ __forceinline__ uint32_t quant_exp(const uint32_t *colmax_bits, int c)
+{
+    if (!colmax_bits) return 127u;
+    const uint32_t E = (colmax_bits[c] >> 23) & 0xFFu;
+    if (E == 0u || E >= 254u) return 127u;
+    return E < 22u ? 22u : (E > 232u ? 232u : E);
+}
+// row of digit g (0..2) of column c (0..9) in the [32][K] digit matrix
+__device__ __forceinline__ int head8_row(int c, int g) { return 16 * (c / 5) + 5 * g + c % 5; }
+__device__ __forceinline__ float quant_up(uint32_t E) { return __uint_as_float((254u + 21u - E) << 23); }      // 2^(21 - e)
+__device__ __forceinline__ float quant_down(uint32_t E) { return __uint_as_float((E - 21u) << 23); }            // 2^(e - 21)
+// three balanced base-256 digits of q, |q| < 2^22: q = d0 + 256 d1 + 65536 d2, d0, d1 in [-128, 127], |d2| <= 64
+__device__ __forceinline__ void digits3(int q, int8_t &d0, int8_t &d1, int8_t &d2)
+{
+    const int a = ((q + 128) & 255) - 128;
+    const int q1 = (q - a) >> 8;
+    const int b = ((q1 + 128) & 255) - 128;
+    d0 = (int8_t)a; d1 = (int8_t)b; d2 = (int8_t)((q1 - b) >> 8);
+}
+
 inline unsigned grid_for(size_t work, unsigned block, unsigned cap = 148u * 16u) {
     size_t g = (work + block - 1) / block;
     if (g < 1) g = 1;
@@ -312,7 +338,7 @@ void download_B(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets, uint64_t 
 float frobenius(Ctx &c);
 
 // ---- spmm.cu
-void build_csr(Ctx &c);
+void build_csr(Ctx &c, bool head_i8 = true);
 // Z(V x b, column-major, ld=V) = B (B^T X); X column-major ld=V; both on the device.
 void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z);
 
@@ -322,6 +348,11 @@ int head_split_rows(int b);
 void spmm_head_launch(Ctx &c, int b, const uint4 *bits, uint32_t num_mtiles, uint32_t NC, uint32_t nsplit,
                       const __nv_bfloat16 *split, float *out, uint32_t m_valid, bool zero_out, bool force_atomic,
                       cudaStream_t stream);
+
+// ---- spmm_head_i8.cu (the same on tcgen05.mma.kind::i8: plane-masked u8 cells x three s8 digits, s32 accumulation)
+void spmm_head_i8_launch(Ctx &c, int b, const uint4 *bits, uint32_t num_mtiles, uint32_t NSC, uint32_t nsplit,
+                         const int8_t *digits, const uint32_t *colmax_bits, float *out, uint32_t m_valid, bool zero_out,
+                         bool force_atomic, cudaStream_t stream);
 
 // ---- panel_tc.cu (tall-skinny panel products of block Gram-Schmidt on tcgen05, split TF32)
 struct PanelTc {

@@ -204,6 +204,16 @@ doc_tail_count_kernel(const int64_t *__restrict__ off, const uint32_t *__restric
 // the order expand_word() (spmm_head.cu) unpacks.
 __device__ __forceinline__ uint32_t head_bit(uint32_t k) { return 1u << (((k & 31u) >> 1) + ((k & 1u) << 4)); }
 
+// int8 head engine (spmm_head_i8.cu): a row's 256-k super-chunk is 8 words; element k sits in word (k >> 2) & 7 at bit
+// 8 (k & 3) + (k >> 5), so that bit j of byte b of word w is k = 32 j + 4 w + b and (word & (0x01010101 << j)) is four
+// cells of MMA j.  Word index of (row m, element k) in a bitmap of NSC super-chunks per 128-row tile:
+__device__ __forceinline__ size_t head8_word(uint32_t m, uint32_t k, uint32_t NSC)
+{
+    return ((((size_t)(m >> 7) * NSC + (k >> 8)) * kHeadTile + (m & 127u)) << 3) + ((k >> 2) & 7u);
+}
+__device__ __forceinline__ uint32_t head8_bit(uint32_t k) { return 1u << (((k & 3u) << 3) + ((k & 255u) >> 5)); }
+
+template <bool I8>
 __global__ void __launch_bounds__(256)
 doc_split_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ row, const uint32_t *__restrict__ rank_of,
                  uint32_t H, uint32_t DB, uint32_t NC1, uint32_t NC2, const int64_t *__restrict__ t1_off,
@@ -224,10 +234,15 @@ doc_split_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ r
                 tail = r >= H;
                 if (!tail) {
                     // bits1: rows = documents, k = rank;  bits2: rows = ranks, k = document
-                    const size_t i1 = ((((size_t)(d >> 7) * NC1 + (r >> 7)) * kHeadTile + (d & 127u)) << 2) + ((r >> 5) & 3u);
-                    const size_t i2 = ((((size_t)(r >> 7) * NC2 + (d >> 7)) * kHeadTile + (r & 127u)) << 2) + ((d >> 5) & 3u);
-                    atomicOr(bits1 + i1, head_bit(r));
-                    atomicOr(bits2 + i2, head_bit(d));
+                    if (I8) {
+                        atomicOr(bits1 + head8_word(d, r, NC1), head8_bit(r));
+                        atomicOr(bits2 + head8_word(r, d, NC2), head8_bit(d));
+                    } else {
+                        const size_t i1 = ((((size_t)(d >> 7) * NC1 + (r >> 7)) * kHeadTile + (d & 127u)) << 2) + ((r >> 5) & 3u);
+                        const size_t i2 = ((((size_t)(r >> 7) * NC2 + (d >> 7)) * kHeadTile + (r & 127u)) << 2) + ((d >> 5) & 3u);
+                        atomicOr(bits1 + i1, head_bit(r));
+                        atomicOr(bits2 + i2, head_bit(d));
+                    }
                 }
             }
             const uint32_t m = __ballot_sync(0xffffffffu, tail);
@@ -254,10 +269,14 @@ rank_rows_copy_kernel(const int64_t *__restrict__ csr_off, const uint32_t *__res
     }
 }
 
-void build_csr(Ctx &c)
+void build_csr(Ctx &c, bool head_i8)
 {
     ISLE_REQUIRE(c.have_B, ISLE_ERR_ARG, "build_csr: build_B first");
-    if (c.have_csr) return;
+    head_i8 = head_i8 && c.opt("spmm_head_i8", 1) != 0;
+    if (c.have_csr && (c.H == 0 || c.head_i8 == head_i8)) return;
+    c.have_csr = false;
+    c.head_i8 = head_i8;
+    const uint32_t kTileK = head_i8 ? 256u : (uint32_t)kHeadChunk;      // K granularity of the head engine
     StatScope s(c, "csr_build", (double)c.nnzB * 24.0);
     const int64_t n = c.nnzB;
     const uint32_t V = (uint32_t)c.V, DB = (uint32_t)c.DB;
@@ -309,11 +328,11 @@ void build_csr(Ctx &c)
         ISLE_CUDA_CHECK(cudaMemcpyAsync(&h0, dcnt.p, 4, cudaMemcpyDeviceToHost, c.stream));
         ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
         const uint32_t hmax = (uint32_t)std::max(0, c.opt("spmm_head_max", 4096));
-        H = std::min(h0, hmax) / kHeadTile * kHeadTile;
+        H = std::min(h0, hmax) / kTileK * kTileK;
     }
     c.H = H;
-    c.DBpad = (DB + kHeadTile - 1) / kHeadTile * kHeadTile;
-    const uint32_t NC1 = H / kHeadChunk, NC2 = c.DBpad / kHeadChunk;
+    c.DBpad = (DB + kTileK - 1) / kTileK * kTileK;
+    const uint32_t NC1 = H / kTileK, NC2 = c.DBpad / kTileK;
 
     // ---- doc-major tail list + head bitmaps
     c.t1_off.alloc((size_t)DB + 1);
@@ -337,8 +356,12 @@ void build_csr(Ctx &c)
         ISLE_CUDA_CHECK(cudaMemsetAsync(c.bits2.p, 0, c.bits2.bytes(), c.stream));
     }
     if (DB) {
-        doc_split_kernel<<<wgrid, 256, 0, c.stream>>>(c.b_off.p, c.b_row.p, c.rank_of.p, H, DB, NC1, NC2, c.t1_off.p, c.t1_idx.p,
-                                                      reinterpret_cast<uint32_t *>(c.bits1.p), reinterpret_cast<uint32_t *>(c.bits2.p));
+        if (head_i8)
+            doc_split_kernel<true><<<wgrid, 256, 0, c.stream>>>(c.b_off.p, c.b_row.p, c.rank_of.p, H, DB, NC1, NC2, c.t1_off.p, c.t1_idx.p,
+                                                                reinterpret_cast<uint32_t *>(c.bits1.p), reinterpret_cast<uint32_t *>(c.bits2.p));
+        else
+            doc_split_kernel<false><<<wgrid, 256, 0, c.stream>>>(c.b_off.p, c.b_row.p, c.rank_of.p, H, DB, NC1, NC2, c.t1_off.p, c.t1_idx.p,
+                                                                 reinterpret_cast<uint32_t *>(c.bits1.p), reinterpret_cast<uint32_t *>(c.bits2.p));
         count_launch(c);
     }
 
@@ -367,12 +390,22 @@ void build_csr(Ctx &c)
     c.xbfp.alloc((size_t)V * 2);
     c.colmax.alloc(kStride);
     c.ybfp.alloc((size_t)std::max<uint32_t>(c.DBpad, 1) * 2);
-    if (H) {
+    c.ycolmax.alloc(kStride);
+    if (H && head_i8) {
+        c.xdig.alloc((size_t)32 * H);           // 3 s8 digits x 10 columns, padded to 32 rows
+        c.ydig.alloc((size_t)32 * c.DBpad);
+        ISLE_CUDA_CHECK(cudaMemsetAsync(c.xdig.p, 0, c.xdig.bytes(), c.stream));
+        ISLE_CUDA_CHECK(cudaMemsetAsync(c.ydig.p, 0, c.ydig.bytes(), c.stream));
+        c.xsplit.release();
+        c.ysplit.release();
+    } else if (H) {
         const size_t nrows = 48;    // 3 bf16 pieces x up to 16 columns
         c.xsplit.alloc(nrows * H);
         c.ysplit.alloc(nrows * c.DBpad);
         ISLE_CUDA_CHECK(cudaMemsetAsync(c.xsplit.p, 0, c.xsplit.bytes(), c.stream));
         ISLE_CUDA_CHECK(cudaMemsetAsync(c.ysplit.p, 0, c.ysplit.bytes(), c.stream));
+        c.xdig.release();
+        c.ydig.release();
     }
     c.have_csr = true;
 }
@@ -492,7 +525,21 @@ __device__ __forceinline__ void bfp_accum5(const uint4 w, float *acc)
 // two lanes loaded, lane (sub & 1) taking unit (sub & 1) of each row with one 16-byte load, so a
 // warp instruction fetches 16 whole sectors.  The two pairs' sums are combined by shuffle; lanes 0 and
 // 1 of the group then own columns 0..4 and 5..9 of the output row (fp32, 16-float stride).
-template <bool ADD>
+// one 16-byte unit of a gathered operand row.  MODE 0: ld.global.nc (allocates an L1 line); 1: L1::no_allocate;
+// 2: L1::evict_first
+template <int MODE>
+__device__ __forceinline__ uint4 ld_row(const uint4 *p)
+{
+    if (MODE == 0) return __ldg(p);
+    uint4 v;
+    if (MODE == 1)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else
+        asm volatile("ld.global.nc.L1::evict_first.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+template <bool ADD, int PIPE>
 __global__ void __launch_bounds__(256)
 spmm_gather_bfp_kernel(const WorkItem *__restrict__ items, size_t n_items, const uint32_t *__restrict__ idx,
                        const uint4 *__restrict__ in, float *__restrict__ out, int b)
@@ -507,14 +554,38 @@ spmm_gather_bfp_kernel(const WorkItem *__restrict__ items, size_t n_items, const
     const uint4 *base = in + u;
     float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     uint32_t j = 0;
-    for (; j + 8 <= len; j += 8) {
-        const uint32_t i0 = ld_idx<true>(p + j + sub), i1 = ld_idx<true>(p + j + 4 + sub);
-        const uint32_t k0 = __shfl_xor_sync(gmask, i0, 1), k1 = __shfl_xor_sync(gmask, i1, 1);
-        // the pair's four rows in stream order: (even lane's, odd lane's) x (first, second load)
-        const uint32_t ra = u ? k0 : i0, rb = u ? i0 : k0, rc = u ? k1 : i1, rd = u ? i1 : k1;
-        const uint4 wa = __ldg(base + (size_t)ra * 2), wb = __ldg(base + (size_t)rb * 2);
-        const uint4 wc = __ldg(base + (size_t)rc * 2), wd = __ldg(base + (size_t)rd * 2);
-        bfp_accum5(wa, acc); bfp_accum5(wb, acc); bfp_accum5(wc, acc); bfp_accum5(wd, acc);
+    if (PIPE == 1) {
+        // software pipeline: the index loads of step j + 1 and the row gathers of step j are in flight while the rows
+        // of step j - 1 are accumulated, so a warp keeps two dependent memory round trips overlapped instead of
+        // serialising them (the kernel is then far less sensitive to how many warps share the SM with it)
+        const uint32_t nfull = len >> 3;
+        uint32_t i0 = 0, i1 = 0;
+        if (nfull) { i0 = ld_idx<true>(p + sub); i1 = ld_idx<true>(p + 4 + sub); }
+        uint4 wa, wb, wc, wd;
+        bool have = false;
+        for (uint32_t s = 0; s < nfull; ++s) {
+            const uint32_t k0 = __shfl_xor_sync(gmask, i0, 1), k1 = __shfl_xor_sync(gmask, i1, 1);
+            const uint32_t ra = u ? k0 : i0, rb = u ? i0 : k0, rc = u ? k1 : i1, rd = u ? i1 : k1;
+            if (s + 1 < nfull) { i0 = ld_idx<true>(p + 8 * (s + 1) + sub); i1 = ld_idx<true>(p + 8 * (s + 1) + 4 + sub); }
+            const uint4 na = __ldg(base + (size_t)ra * 2), nb = __ldg(base + (size_t)rb * 2);
+            const uint4 nc = __ldg(base + (size_t)rc * 2), nd = __ldg(base + (size_t)rd * 2);
+            if (have) { bfp_accum5(wa, acc); bfp_accum5(wb, acc); bfp_accum5(wc, acc); bfp_accum5(wd, acc); }
+            wa = na; wb = nb; wc = nc; wd = nd;
+            have = true;
+        }
+        if (have) { bfp_accum5(wa, acc); bfp_accum5(wb, acc); bfp_accum5(wc, acc); bfp_accum5(wd, acc); }
+        j = nfull << 3;
+    } else {
+        for (; j + 8 <= len; j += 8) {
+            const uint32_t i0 = ld_idx<true>(p + j + sub), i1 = ld_idx<true>(p + j + 4 + sub);
+            const uint32_t k0 = __shfl_xor_sync(gmask, i0, 1), k1 = __shfl_xor_sync(gmask, i1, 1);
+            // the pair's four rows in stream order: (even lane's, odd lane's) x (first, second load)
+            const uint32_t ra = u ? k0 : i0, rb = u ? i0 : k0, rc = u ? k1 : i1, rd = u ? i1 : k1;
+            constexpr int M = PIPE == 2 ? 1 : (PIPE == 3 ? 2 : 0);
+            const uint4 wa = ld_row<M>(base + (size_t)ra * 2), wb = ld_row<M>(base + (size_t)rb * 2);
+            const uint4 wc = ld_row<M>(base + (size_t)rc * 2), wd = ld_row<M>(base + (size_t)rd * 2);
+            bfp_accum5(wa, acc); bfp_accum5(wb, acc); bfp_accum5(wc, acc); bfp_accum5(wd, acc);
+        }
     }
     if (j < len) {
         const uint32_t n = len - j;     // 1..7 left: positions sub and 4 + sub
@@ -553,27 +624,35 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16 &h, __nv_bfloat16 
     l = __float2bfloat16_rn(r2);
 }
 
-// colmax_bits[j] = bit pattern of max_w |X[w + j ld]| (non-negative floats order like unsigned integers)
-__global__ void __launch_bounds__(256)
-colmax_kernel(const float *__restrict__ X, size_t ld, uint32_t n, int b, uint32_t *__restrict__ colmax_bits)
+// colmax_bits[j] = bit pattern of max_w |scale[w] X[w + j ld]| (non-negative floats order like unsigned integers): the
+// column maxima of the operand rows as the passes see them (Xs = diag(sqrt_zeta) X)
+__global__ void __launch_bounds__(1024)
+colmax_kernel(const float *__restrict__ X, size_t ld, uint32_t n, int b, const float *__restrict__ scale,
+              uint32_t *__restrict__ colmax_bits)
 {
     float m[kStride];
 #pragma unroll
     for (int j = 0; j < kStride; ++j) m[j] = 0.f;
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+        const float s = scale ? scale[w] : 1.0f;
 #pragma unroll
         for (int j = 0; j < kStride; ++j)
-            if (j < b) m[j] = fmaxf(m[j], fabsf(X[w + (size_t)j * ld]));
+            if (j < b) m[j] = fmaxf(m[j], fabsf(s * X[w + (size_t)j * ld]));
     }
+    __shared__ uint32_t smax[kStride];
+    if (threadIdx.x < kStride) smax[threadIdx.x] = 0u;
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < kStride; ++j) {
         if (j < b) {
             float v = m[j];
 #pragma unroll
             for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-            if ((threadIdx.x & 31) == 0 && v > 0.f) atomicMax(colmax_bits + j, __float_as_uint(v));
+            if ((threadIdx.x & 31) == 0 && v > 0.f) atomicMax(smax + j, __float_as_uint(v));
         }
     }
+    __syncthreads();
+    if (threadIdx.x < b && smax[threadIdx.x]) atomicMax(colmax_bits + threadIdx.x, smax[threadIdx.x]);     // one atomic per column per CTA
 }
 
 // Exact power-of-two column equilibration for the block-FP rows: columns that share a unit get the same
@@ -591,7 +670,8 @@ __device__ __forceinline__ float col_pow2(uint32_t colmax_bits, bool up)
 __global__ void __launch_bounds__(256)
 pack_scaled_kernel(const float *__restrict__ X, size_t ld, uint32_t n, int b, const float *__restrict__ scale,
                    const uint32_t *__restrict__ word_of_rank, float4 *__restrict__ out, uint4 *__restrict__ out_bfp,
-                   const uint32_t *__restrict__ colmax_bits, uint32_t H, int BS, __nv_bfloat16 *__restrict__ xsplit)
+                   const uint32_t *__restrict__ colmax_bits, uint32_t H, int BS, __nv_bfloat16 *__restrict__ xsplit,
+                   int8_t *__restrict__ xdig)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
@@ -600,7 +680,7 @@ pack_scaled_kernel(const float *__restrict__ X, size_t ld, uint32_t n, int b, co
     float v[kStride];
 #pragma unroll
     for (int j = 0; j < kStride; ++j)
-        v[j] = (j < b) ? s * (X[w + (size_t)j * ld] * (colmax_bits ? col_pow2(colmax_bits[j], false) : 1.0f)) : 0.0f;
+        v[j] = (j < b) ? (s * X[w + (size_t)j * ld]) * (colmax_bits ? col_pow2(colmax_bits[j], false) : 1.0f) : 0.0f;
     if (out_bfp) {      // b <= 10: one-sector rows
         out_bfp[(size_t)r * 2] = bfp_encode5(v);
         out_bfp[(size_t)r * 2 + 1] = bfp_encode5(v + 5);
@@ -609,7 +689,19 @@ pack_scaled_kernel(const float *__restrict__ X, size_t ld, uint32_t n, int b, co
         for (int q = 0; q < 4; ++q)
             out[(size_t)r * 4 + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
-    if (r < H) {
+    if (r < H && xdig) {
+        // int8 head engine: the equilibrated values (column max in [1, 2)) as 22-bit integers, three s8 digits, K-major
+#pragma unroll
+        for (int j = 0; j < kStride; ++j) {
+            if (j < b) {
+                int8_t d0, d1, d2;
+                digits3(__float2int_rn(v[j] * 2097152.0f), d0, d1, d2);
+                xdig[(size_t)head8_row(j, 0) * H + r] = d0;
+                xdig[(size_t)head8_row(j, 1) * H + r] = d1;
+                xdig[(size_t)head8_row(j, 2) * H + r] = d2;
+            }
+        }
+    } else if (r < H) {
 #pragma unroll
         for (int j = 0; j < kStride; ++j) {
             if (j < b) {
@@ -623,11 +715,44 @@ pack_scaled_kernel(const float *__restrict__ X, size_t ld, uint32_t n, int b, co
     }
 }
 
+// ycolmax_bits[j] = bit pattern of max_d |Y[d, j]| over the padded row-major rows of Y
+__global__ void __launch_bounds__(1024)
+rowmajor_colmax_kernel(const float4 *__restrict__ Y, uint32_t DB, int b, uint32_t *__restrict__ colmax_bits)
+{
+    float m[kStride];
+#pragma unroll
+    for (int j = 0; j < kStride; ++j) m[j] = 0.f;
+    for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < DB; d += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (4 * q < b) {
+                const float4 t = Y[(size_t)d * 4 + q];
+                m[4 * q] = fmaxf(m[4 * q], fabsf(t.x)); m[4 * q + 1] = fmaxf(m[4 * q + 1], fabsf(t.y));
+                m[4 * q + 2] = fmaxf(m[4 * q + 2], fabsf(t.z)); m[4 * q + 3] = fmaxf(m[4 * q + 3], fabsf(t.w));
+            }
+        }
+    }
+    __shared__ uint32_t smax[kStride];
+    if (threadIdx.x < kStride) smax[threadIdx.x] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kStride; ++j) {
+        if (j < b) {
+            float v = m[j];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if ((threadIdx.x & 31) == 0 && v > 0.f) atomicMax(smax + j, __float_as_uint(v));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < b && smax[threadIdx.x]) atomicMax(colmax_bits + threadIdx.x, smax[threadIdx.x]);     // one atomic per column per CTA
+}
+
 // ysplit[(piece*BS + j) * DBpad + d] = pieces of Y[d, j] (head engine, when ysplit != NULL);
 // ybfp[d] = one-sector copy of Y[d, :] (tail gather of pass 2, when ybfp != NULL)
 __global__ void __launch_bounds__(256)
 ysplit_kernel(const float4 *__restrict__ Y, uint32_t DB, uint32_t DBpad, int b, int BS, __nv_bfloat16 *__restrict__ ysplit,
-              uint4 *__restrict__ ybfp)
+              uint4 *__restrict__ ybfp, int8_t *__restrict__ ydig, const uint32_t *__restrict__ ycolmax_bits)
 {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= DB) return;
@@ -640,6 +765,19 @@ ysplit_kernel(const float4 *__restrict__ Y, uint32_t DB, uint32_t DBpad, int b, 
     if (ybfp) {
         ybfp[(size_t)d * 2] = bfp_encode5(v);
         ybfp[(size_t)d * 2 + 1] = bfp_encode5(v + 5);
+    }
+    if (ydig) {      // int8 head engine: quantised with the column maxima of Y
+#pragma unroll
+        for (int j = 0; j < kStride; ++j) {
+            if (j < b) {
+                int8_t d0, d1, d2;
+                digits3(__float2int_rn(v[j] * quant_up(quant_exp(ycolmax_bits, j))), d0, d1, d2);
+                ydig[(size_t)head8_row(j, 0) * DBpad + d] = d0;
+                ydig[(size_t)head8_row(j, 1) * DBpad + d] = d1;
+                ydig[(size_t)head8_row(j, 2) * DBpad + d] = d2;
+            }
+        }
+        return;
     }
     if (!ysplit) return;
 #pragma unroll
@@ -699,12 +837,21 @@ static void launch_gather(Ctx &c, int nch, bool add, const WorkItem *items, size
 }
 
 static void launch_gather_bfp(Ctx &c, int b, bool add, const WorkItem *items, size_t n_items, const uint32_t *idx,
-                              const uint4 *in, float *out)
+                              const uint4 *in, float *out, cudaStream_t stream = nullptr)
 {
     if (!n_items) return;
+    if (!stream) stream = c.stream;
     const unsigned grid = (unsigned)((n_items * 4 + 255) / 256);
-    if (add) spmm_gather_bfp_kernel<true><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in, out, b);
-    else spmm_gather_bfp_kernel<false><<<grid, 256, 0, c.stream>>>(items, n_items, idx, in, out, b);
+    const int pipe = c.opt("spmm_tail_pipe", 0);      // 0 plain, 1 software pipeline, 2 rows with L1::no_allocate, 3 rows with L1::evict_first
+    const int carve = c.opt("spmm_tail_carveout", -1);      // experiment: shared-memory carve-out the gather kernel asks for (percent)
+#define ISLE_BFP_LAUNCH(A, P)                                                                                             \
+    do {                                                                                                                  \
+        if (carve >= 0) cudaFuncSetAttribute(spmm_gather_bfp_kernel<A, P>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
+        spmm_gather_bfp_kernel<A, P><<<grid, 256, 0, stream>>>(items, n_items, idx, in, out, b);                          \
+    } while (0)
+    if (add) { if (pipe == 1) ISLE_BFP_LAUNCH(true, 1); else if (pipe == 2) ISLE_BFP_LAUNCH(true, 2); else if (pipe == 3) ISLE_BFP_LAUNCH(true, 3); else ISLE_BFP_LAUNCH(true, 0); }
+    else { if (pipe == 1) ISLE_BFP_LAUNCH(false, 1); else if (pipe == 2) ISLE_BFP_LAUNCH(false, 2); else if (pipe == 3) ISLE_BFP_LAUNCH(false, 3); else ISLE_BFP_LAUNCH(false, 0); }
+#undef ISLE_BFP_LAUNCH
     count_launch(c);
 }
 
@@ -712,43 +859,59 @@ void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z)
 {
     ISLE_REQUIRE(c.have_B, ISLE_ERR_ARG, "spsptr_multiply: build_B first");
     ISLE_REQUIRE(b >= 1 && b <= kStride, ISLE_ERR_ARG, "spsptr_multiply: block size must be in [1,16]");
-    build_csr(c);
+    // block sizes <= 10 gather one-sector (32-byte) operand rows; wider blocks use padded fp32 rows
+    const bool bfp = b <= 10 && c.opt("spmm_bfp", 1) != 0;
+    // the int8 head engine needs the column equilibration of the block-FP path and N = 3 x 10 columns
+    build_csr(c, bfp);
     const uint32_t V = (uint32_t)c.V, DB = (uint32_t)c.DB, H = c.H;
+    const bool i8 = H && c.head_i8;
     const int nch = (b + 3) / 4;
     const int BS = head_block_stride(b);
     c.counters["ks_ops"] += 1.0;
 
-    // block sizes <= 10 gather one-sector (32-byte) operand rows; wider blocks use padded fp32 rows
-    const bool bfp = b <= 10 && c.opt("spmm_bfp", 1) != 0;
     if (bfp) {
         ISLE_CUDA_CHECK(cudaMemsetAsync(c.colmax.p, 0, c.colmax.bytes(), c.stream));
-        colmax_kernel<<<std::min<unsigned>((V + 255) / 256, (unsigned)c.num_sms * 2), 256, 0, c.stream>>>(X, (size_t)V, V, b, c.colmax.p);
+        colmax_kernel<<<std::min<unsigned>((V + 1023) / 1024, (unsigned)c.num_sms), 1024, 0, c.stream>>>(X, (size_t)V, V, b, c.sqrt_zeta.p, c.colmax.p);
         count_launch(c);
     }
     pack_scaled_kernel<<<(V + 255) / 256, 256, 0, c.stream>>>(X, (size_t)V, V, b, c.sqrt_zeta.p, c.word_of_rank.p,
                                                                reinterpret_cast<float4 *>(c.xs.p), bfp ? c.xbfp.p : nullptr,
-                                                               bfp ? c.colmax.p : nullptr, H, BS, c.xsplit.p);
+                                                               bfp ? c.colmax.p : nullptr, H, BS, c.xsplit.p, i8 ? c.xdig.p : nullptr);
     count_launch(c);
     // T is always zeroed: word rows are split routinely and the head adds partial sums atomically.
     ISLE_CUDA_CHECK(cudaMemsetAsync(c.zbuf.p, 0, c.zbuf.bytes(), c.stream));
+    // head engine of pass 1 (rows = documents, K = head ranks) / pass 2 (rows = head ranks, K = documents)
+    auto head1 = [&](bool zero_out, bool force_atomic, cudaStream_t st) {
+        if (i8) spmm_head_i8_launch(c, b, c.bits1.p, c.DBpad / kHeadTile, H / 256, 1, c.xdig.p, nullptr, c.ybuf.p, DB, zero_out, force_atomic, st);
+        else spmm_head_launch(c, b, c.bits1.p, c.DBpad / kHeadTile, H / kHeadChunk, 1, c.xsplit.p, c.ybuf.p, DB, zero_out, force_atomic, st);
+    };
+    auto head2 = [&](cudaStream_t st) {
+        const uint32_t mt = H / kHeadTile;
+        // K (documents) split over jobs: whole waves of jobs over the SMs
+        const uint32_t nsplit = std::max<uint32_t>(1, ((uint32_t)c.num_sms * (uint32_t)std::max(1, c.opt("spmm_head2_waves", 1))) / mt);
+        if (i8) spmm_head_i8_launch(c, b, c.bits2.p, mt, c.DBpad / 256, nsplit, c.ydig.p, c.ycolmax.p, c.zbuf.p, H, false, false, st);
+        else spmm_head_launch(c, b, c.bits2.p, mt, c.DBpad / kHeadChunk, nsplit, c.ysplit.p, c.zbuf.p, H, false, false, st);
+    };
     {
         // bytes_pass = nnz*4 + (rows+1)*8 + dense_in*4 + dense_out*4
         StatScope s(c, "spmm_bt", (double)c.nnzB * 4.0 + ((double)DB + 1) * 8.0 + ((double)V + DB) * b * 4.0,
                     2.0 * c.nnzB * b);
         if (H && bfp && c.opt("spmm_fork", 1) != 0) {
-            // head and tail add into a zeroed Y side by side (tensor pipe + ALU vs L1TEX-bound gathers)
+            // head and tail add into a zeroed Y side by side (TMEM / tensor pipe vs L1TEX-bound gathers).  The head goes
+            // first, on the main stream directly behind the memset, so that its one persistent CTA per SM is placed
+            // before the tail's thousands of small CTAs fill every SM (a head launched second would wait for them all).
             ISLE_CUDA_CHECK(cudaMemsetAsync(c.ybuf.p, 0, c.ybuf.bytes(), c.stream));
             ISLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
             ISLE_CUDA_CHECK(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
-            spmm_head_launch(c, b, c.bits1.p, c.DBpad / kHeadTile, H / kHeadChunk, 1, c.xsplit.p, c.ybuf.p, DB, false, true, c.stream2);
+            head1(false, true, c.stream);
+            launch_gather_bfp(c, b, true, c.items_bt.p, c.n_items_bt, c.t1_idx.p, c.xbfp.p, c.ybuf.p, c.stream2);
             ISLE_CUDA_CHECK(cudaEventRecord(c.ev_join, c.stream2));
-            launch_gather_bfp(c, b, true, c.items_bt.p, c.n_items_bt, c.t1_idx.p, c.xbfp.p, c.ybuf.p);
             ISLE_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
         } else if (H) {
             {
                 StatScope sh(c, "spmm_head1");
                 // every row of Y is written (store mode): Y = head part
-                spmm_head_launch(c, b, c.bits1.p, c.DBpad / kHeadTile, H / kHeadChunk, 1, c.xsplit.p, c.ybuf.p, DB, true, false, c.stream);
+                head1(true, false, c.stream);
             }
             StatScope st(c, "spmm_tail1");
             if (bfp) launch_gather_bfp(c, b, true, c.items_bt.p, c.n_items_bt, c.t1_idx.p, c.xbfp.p, c.ybuf.p);
@@ -764,27 +927,37 @@ void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z)
         StatScope s(c, "spmm_b", (double)c.nnzB * 4.0 + ((double)V + 1) * 8.0 + ((double)V + DB) * b * 4.0,
                     2.0 * c.nnzB * b);
         if ((H || bfp) && DB) {
+            if (i8) {      // quantisation scale of Y: its column maxima
+                ISLE_CUDA_CHECK(cudaMemsetAsync(c.ycolmax.p, 0, c.ycolmax.bytes(), c.stream));
+                rowmajor_colmax_kernel<<<std::min<unsigned>((DB + 1023) / 1024, (unsigned)c.num_sms), 1024, 0, c.stream>>>(
+                    reinterpret_cast<const float4 *>(c.ybuf.p), DB, b, c.ycolmax.p);
+                count_launch(c);
+            }
             ysplit_kernel<<<(DB + 255) / 256, 256, 0, c.stream>>>(reinterpret_cast<const float4 *>(c.ybuf.p), DB, c.DBpad, b, BS,
-                                                                  H ? c.ysplit.p : nullptr, bfp ? c.ybfp.p : nullptr);
+                                                                  (H && !i8) ? c.ysplit.p : nullptr, bfp ? c.ybfp.p : nullptr,
+                                                                  i8 ? c.ydig.p : nullptr, c.ycolmax.p);
             count_launch(c);
         }
         if (H) {
-            const uint32_t mt = H / kHeadTile, NC2 = c.DBpad / kHeadChunk;
-            const uint32_t nsplit = std::max<uint32_t>(1, (uint32_t)c.num_sms / mt);   // one wave of jobs
             const bool fork = c.opt("spmm_fork", 1) != 0;
             if (fork) {
                 // the head and the tail of pass 2 write disjoint rows of T: run them side by side
                 ISLE_CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
                 ISLE_CUDA_CHECK(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
-                spmm_head_launch(c, b, c.bits2.p, mt, NC2, nsplit, c.ysplit.p, c.zbuf.p, H, false, false, c.stream2);
-                ISLE_CUDA_CHECK(cudaEventRecord(c.ev_join, c.stream2));
-                if (bfp) launch_gather_bfp(c, b, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybfp.p, c.zbuf.p);
-                else launch_gather(c, nch, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybuf.p, c.zbuf.p);
+                if (bfp) {      // head first on the main stream (see pass 1), tail beside it
+                    head2(c.stream);
+                    launch_gather_bfp(c, b, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybfp.p, c.zbuf.p, c.stream2);
+                    ISLE_CUDA_CHECK(cudaEventRecord(c.ev_join, c.stream2));
+                } else {
+                    head2(c.stream2);
+                    ISLE_CUDA_CHECK(cudaEventRecord(c.ev_join, c.stream2));
+                    launch_gather(c, nch, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybuf.p, c.zbuf.p);
+                }
                 ISLE_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
             } else {
                 {
                     StatScope sh(c, "spmm_head2");
-                    spmm_head_launch(c, b, c.bits2.p, mt, NC2, nsplit, c.ysplit.p, c.zbuf.p, H, false, false, c.stream);
+                    head2(c.stream);
                 }
                 StatScope st(c, "spmm_tail2");
                 if (bfp) launch_gather_bfp(c, b, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybfp.p, c.zbuf.p);

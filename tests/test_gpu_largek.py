@@ -303,9 +303,10 @@ def test_operator_engines_at_c2_size(ctx):
     X = np.random.default_rng(1).standard_normal((c.V, 10)).astype(np.float32)
     Zr = Bm @ (Bm.T @ X.astype(np.float64))
     scale = np.max(np.abs(Zr), axis=0)
-    defaults = dict(spmm_head=1, spmm_bfp=1, spmm_fork=1, spmm_head_density_ppm=12000)
+    defaults = dict(spmm_head=1, spmm_bfp=1, spmm_fork=1, spmm_head_density_ppm=12000, spmm_head_i8=1, spmm_head8_slab=8)
     try:
-        for opts in (dict(spmm_head=0, spmm_bfp=0), dict(spmm_head=0), dict(spmm_fork=0), dict(), dict(spmm_head_density_ppm=4000)):
+        for opts in (dict(spmm_head=0, spmm_bfp=0), dict(spmm_head=0), dict(spmm_fork=0), dict(), dict(spmm_head_density_ppm=4000),
+                     dict(spmm_head_i8=0), dict(spmm_head8_slab=3, spmm_head_density_ppm=4000)):
             for k_, v_ in {**defaults, **opts}.items():
                 ctx.set_option(k_, v_)
             Z = B.multiply(X)

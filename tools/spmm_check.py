@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--seg", type=int, nargs="*", default=[16])
     ap.add_argument("--only-head-serial", action="store_true")
+    ap.add_argument("--i8", type=int, nargs="*", default=[1])
+    ap.add_argument("--head-max", type=int, default=4096)
+    ap.add_argument("--opt", nargs="*", default=[], help="extra name=value options")
     a = ap.parse_args()
 
     import torch
@@ -91,16 +94,21 @@ def main():
     if not a.only_head_serial:
         ctx.set_option("spmm_head", 0)
         run("gather only", a.reps)
-    for ppm, seg in [(p_, s_) for p_ in a.density_ppm for s_ in a.seg]:
+    ctx.set_option("spmm_head_max", a.head_max)
+    for o in a.opt:
+        k_, v_ = o.split("=")
+        ctx.set_option(k_, int(v_))
+    for ppm, seg, i8 in [(p_, s_, i_) for i_ in a.i8 for p_ in a.density_ppm for s_ in a.seg]:
+        ctx.set_option("spmm_head_i8", i8)
         ctx.set_option("spmm_head_seg", seg)
         ctx.set_option("spmm_head", 1)
         ctx.set_option("spmm_head_density_ppm", ppm)
         ctx.set_option("spmm_fork", 0)
-        run(f"head {ppm}ppm seg{seg} serial", a.reps)
+        run(f"head {ppm}ppm seg{seg} i8={i8} serial", a.reps)
         if a.only_head_serial:
             continue
         ctx.set_option("spmm_fork", 1)
-        run(f"head {ppm}ppm seg{seg} fork", a.reps)
+        run(f"head {ppm}ppm seg{seg} i8={i8} fork", a.reps)
     ctx.close()
 
 
