@@ -297,27 +297,32 @@ struct StatScope {
 
 inline void count_launch(Ctx &c, int n = 1) { c.launches += n; }
 
-// Quantisation of a dense operand column for the int8 head engine (spmm_head_i8.cu): q = rn(x * 2^(21 - e)) with
-// 2^e <= column max < 2^(e+1), so |q| < 2^22 fits three balanced base-256 digits; the value is q * 2^(e - 21).
+// Quantisation of a dense operand column for the int8 head engine (spmm_head_i8.cu): q = rn(x * 2^(29 - e)) with
+// 2^e <= column max < 2^(e+1), so |q| < 2^30 fits four balanced base-256 digits; the value is q * 2^(e - 29).
 // `colmax_bits` = bit pattern of the column's max |x| (NULL / 0 / non-finite: e = 0).  Returns the biased exponent.
 __device__ __forceinline__ uint32_t quant_exp(const uint32_t *colmax_bits, int c)
 {
     if (!colmax_bits) return 127u;
     const uint32_t E = (colmax_bits[c] >> 23) & 0xFFu;
     if (E == 0u || E >= 254u) return 127u;
-    return E < 22u ? 22u : (E > 232u ? 232u : E);
+    return E < 30u ? 30u : (E > 224u ? 224u : E);
 }
-// row of digit g (0..2) of column c (0..9) in the [32][K] digit matrix
-__device__ __forceinline__ int head8_row(int c, int g) { return 16 * (c / 5) + 5 * g + c % 5; }
-__device__ __forceinline__ float quant_up(uint32_t E) { return __uint_as_float((254u + 21u - E) << 23); }      // 2^(21 - e)
-__device__ __forceinline__ float quant_down(uint32_t E) { return __uint_as_float((E - 21u) << 23); }            // 2^(e - 21)
-// three balanced base-256 digits of q, |q| < 2^22: q = d0 + 256 d1 + 65536 d2, d0, d1 in [-128, 127], |d2| <= 64
-__device__ __forceinline__ void digits3(int q, int8_t &d0, int8_t &d1, int8_t &d2)
+constexpr int kHead8Rows = 40;      // rows of the digit matrix of the int8 head engine (10 columns x 4 digits)
+// row of digit g (0..3) of column c (0..9) in the [40][K] digit matrix: columns 0-3 and 4-7 as 4 x 4 blocks of 16 rows,
+// columns 8-9 as a 2 x 4 block of 8 rows
+__device__ __forceinline__ int head8_row(int c, int g) { return c < 8 ? 16 * (c / 4) + 4 * g + c % 4 : 32 + 2 * g + (c - 8); }
+__device__ __forceinline__ float quant_up(uint32_t E) { return __uint_as_float((254u + 29u - E) << 23); }      // 2^(29 - e)
+__device__ __forceinline__ float quant_down(uint32_t E) { return __uint_as_float((E - 29u) << 23); }            // 2^(e - 29)
+// four balanced base-256 digits of q, |q| <= 2^30: q = d0 + 2^8 d1 + 2^16 d2 + 2^24 d3, d0..d2 in [-128, 127], |d3| <= 64
+__device__ __forceinline__ void digits4(int q, int8_t *d)
 {
-    const int a = ((q + 128) & 255) - 128;
-    const int q1 = (q - a) >> 8;
-    const int b = ((q1 + 128) & 255) - 128;
-    d0 = (int8_t)a; d1 = (int8_t)b; d2 = (int8_t)((q1 - b) >> 8);
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        const int a = ((q + 128) & 255) - 128;
+        d[g] = (int8_t)a;
+        q = (q - a) >> 8;
+    }
+    d[3] = (int8_t)q;
 }
 
 inline unsigned grid_for(size_t work, unsigned block, unsigned cap = 148u * 16u) {

@@ -392,8 +392,8 @@ void build_csr(Ctx &c, bool head_i8)
     c.ybfp.alloc((size_t)std::max<uint32_t>(c.DBpad, 1) * 2);
     c.ycolmax.alloc(kStride);
     if (H && head_i8) {
-        c.xdig.alloc((size_t)32 * H);           // 3 s8 digits x 10 columns, padded to 32 rows
-        c.ydig.alloc((size_t)32 * c.DBpad);
+        c.xdig.alloc((size_t)kHead8Rows * H);           // 4 s8 digits x 10 columns in three groups of 16 rows
+        c.ydig.alloc((size_t)kHead8Rows * c.DBpad);
         ISLE_CUDA_CHECK(cudaMemsetAsync(c.xdig.p, 0, c.xdig.bytes(), c.stream));
         ISLE_CUDA_CHECK(cudaMemsetAsync(c.ydig.p, 0, c.ydig.bytes(), c.stream));
         c.xsplit.release();
@@ -690,15 +690,14 @@ pack_scaled_kernel(const float *__restrict__ X, size_t ld, uint32_t n, int b, co
             out[(size_t)r * 4 + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
     if (r < H && xdig) {
-        // int8 head engine: the equilibrated values (column max in [1, 2)) as 22-bit integers, three s8 digits, K-major
+        // int8 head engine: the equilibrated values (column max in [1, 2)) as 30-bit integers, four s8 digits, K-major
 #pragma unroll
         for (int j = 0; j < kStride; ++j) {
             if (j < b) {
-                int8_t d0, d1, d2;
-                digits3(__float2int_rn(v[j] * 2097152.0f), d0, d1, d2);
-                xdig[(size_t)head8_row(j, 0) * H + r] = d0;
-                xdig[(size_t)head8_row(j, 1) * H + r] = d1;
-                xdig[(size_t)head8_row(j, 2) * H + r] = d2;
+                int8_t dg[4];
+                digits4(__float2int_rn(v[j] * 536870912.0f), dg);      // |v| < 2: |q| <= 2^30
+#pragma unroll
+                for (int g = 0; g < 4; ++g) xdig[(size_t)head8_row(j, g) * H + r] = dg[g];
             }
         }
     } else if (r < H) {
@@ -770,11 +769,10 @@ ysplit_kernel(const float4 *__restrict__ Y, uint32_t DB, uint32_t DBpad, int b, 
 #pragma unroll
         for (int j = 0; j < kStride; ++j) {
             if (j < b) {
-                int8_t d0, d1, d2;
-                digits3(__float2int_rn(v[j] * quant_up(quant_exp(ycolmax_bits, j))), d0, d1, d2);
-                ydig[(size_t)head8_row(j, 0) * DBpad + d] = d0;
-                ydig[(size_t)head8_row(j, 1) * DBpad + d] = d1;
-                ydig[(size_t)head8_row(j, 2) * DBpad + d] = d2;
+                int8_t dg[4];
+                digits4(__float2int_rn(v[j] * quant_up(quant_exp(ycolmax_bits, j))), dg);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) ydig[(size_t)head8_row(j, g) * DBpad + d] = dg[g];
             }
         }
         return;

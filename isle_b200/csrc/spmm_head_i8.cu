@@ -12,9 +12,10 @@
 //               cells).  A set cell of bit-plane p = j & 3 carries the value 2^p instead of 1, so the eight
 //               MMAs of a super-chunk (one per j, K = 32 cells each) accumulate into the accumulator of their
 //               plane and the epilogue adds the four planes as acc_p >> p (exact: acc_p is a multiple of 2^p).
-//   B operand   the dense operand quantised per column to 22 bits (q = rn(x 2^(21 - E)), 2^E <= column max <
-//               2^(E+1)) and split into three balanced base-256 digits, s8, K-major, staged by TMA (128-byte
-//               swizzle); N = 32: two halves of 16 rows, each five columns x 3 digits (+ 1 unused).
+//   B operand   the dense operand quantised per column to 30 bits (q = rn(x 2^(29 - E)), 2^E <= column max <
+//               2^(E+1): every entry within 2^-6 of its column maximum is represented EXACTLY, smaller ones to
+//               2^-30 of the maximum) and split into four balanced base-256 digits, s8, K-major, staged by TMA
+//               (128-byte swizzle); 40 rows: columns 0-3 and 4-7 as 4 x 4 blocks, columns 8-9 as a 2 x 4 block.
 //   D           s32 in TMEM (tcgen05.mma.kind::i8): integer accumulation is exact, so there is no bound on
 //               the length of an accumulation chain other than overflow (segments of <= 65536 cells).
 //
@@ -47,13 +48,16 @@ using namespace tcptx;
 
 constexpr uint32_t kG = 2;                       // worker groups = accumulator sets
 constexpr uint32_t kP = 2;                       // bit planes kept in separate accumulators (cell values 1, 2)
-constexpr uint32_t kN = 32;                      // UMMA N: two halves of five columns x 3 digits (+ 1 unused row each)
-constexpr uint32_t kAccCols = kG * kP * kN;      // accumulator sets at kP * kN * set
+constexpr uint32_t kN = 48;                      // UMMA N (multiple of 16); the digit matrix has kHead8Rows = 40 rows (head8_row), the
+                                                 // MMA's rows 40..47 read whatever follows the tile and land in accumulator columns nobody reads
+constexpr uint32_t kPS = 64;                     // TMEM column stride of one plane accumulator (48 used; power-of-two aligned)
+constexpr uint32_t kAccCols = kG * kP * kPS;     // accumulator sets at kP * kPS * set
 constexpr uint32_t kA = (512 - kAccCols) / 64;   // A stages in TMEM behind them: super-chunk n uses stage n % kA, expanded by group n % 2
+static_assert(kA % kG == 0, "an A stage must always be filled by the same worker group (parity waits skip no phase)");
 constexpr uint32_t kWarpMma = 4 * kG, kWarpTma = 4 * kG + 1;
 constexpr int kThreads = 32 * (4 * kG + 2);
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kBoxBytes = kN * 128;         // one swizzled [32 rows x 128 k] s8 tile
+constexpr uint32_t kBoxBytes = kHead8Rows * 128; // one swizzled [40 rows x 128 k] s8 tile (5 swizzle atoms of 8 rows)
 constexpr uint32_t kScBytes = 2 * kBoxBytes;     // digits of one 256-k super-chunk
 constexpr uint32_t kBitBytes = kHeadTile * 32;   // 128 rows x 256 bits
 constexpr uint32_t kSpinLimit = 1u << 17;
@@ -238,7 +242,7 @@ spmm_head_i8_kernel(const __grid_constant__ CUtensorMap map_b, const Head8Params
                 const uint32_t c0 = (uint32_t)((uint64_t)p.NSC * sl / p.nslabs), c1 = (uint32_t)((uint64_t)p.NSC * (sl + 1) / p.nslabs);
                 if (resident && sl != cur_slab) { mbar_wait(slab_full, sphase, 0x22, job, sl); sphase ^= 1; cur_slab = sl; }
                 mbar_wait(&acc_empty[buf], bphase ^ 1, 0x20, job, c0);
-                const uint32_t d_tmem = tmem_base + buf * (kP * kN);
+                const uint32_t d_tmem = tmem_base + buf * (kP * kPS);
                 for (uint32_t sc = c0; sc < c1; ++sc) {
                     if (resident) mbar_wait(&a_full[a], aphase, 0x21, job, sc);
                     else mbar_wait2(&full[stage], phase, &a_full[a], aphase, 0x21, job, sc);
@@ -251,7 +255,7 @@ spmm_head_i8_kernel(const __grid_constant__ CUtensorMap map_b, const Head8Params
                     for (uint32_t j = 0; j < 8; ++j) {
                         // MMA j: k = 32 j .. 32 j + 31 of the super-chunk = TMEM columns 8 j .. 8 j + 7 of the A
                         // stage (cells worth 2^(j % kP)), 32 bytes along K of digit tile j >> 2
-                        umma_i8_ts(d_tmem + (j & (kP - 1)) * kN, a_tmem + j * 8,
+                        umma_i8_ts(d_tmem + (j & (kP - 1)) * kPS, a_tmem + j * 8,
                                    bd + (uint64_t)((j >> 2) * (kBoxBytes >> 4) + (j & 3) * 2), idesc, j >= kP ? 1u : later);
                     }
                     if (!resident) { umma_commit(&empty[stage]); if (++stage == p.stages) { stage = 0; phase ^= 1; } }
@@ -278,30 +282,34 @@ spmm_head_i8_kernel(const __grid_constant__ CUtensorMap map_b, const Head8Params
         auto drain = [&]() {
             mbar_wait(&acc_full[pend_buf], pend_phase, 0x30 + grp, pend_row, pend_buf * 2 + pend_phase);
             tc_fence_after();
-            // digit g of column c sits at n = head8_row(c, g) = 16 (c / 5) + 5 g + c % 5: each 16-column half of the
-            // accumulator holds five output columns completely
+            // digit g of column c sits at n = head8_row(c, g): columns 0-3 in accumulator columns [0, 16), 4-7 in
+            // [16, 32) (n = 16 (c / 4) + 4 g + c % 4), columns 8, 9 in [32, 40) (n = 32 + 2 g + c - 8)
             float v[16];
 #pragma unroll
             for (int c = 10; c < 16; ++c) v[c] = 0.0f;
 #pragma unroll
-            for (uint32_t h = 0; h < 2; ++h) {
+            for (uint32_t h = 0; h < 3; ++h) {
                 int S[16];
 #pragma unroll
                 for (uint32_t n = 0; n < 16; ++n) S[n] = 0;
 #pragma unroll
                 for (uint32_t pl = 0; pl < kP; ++pl) {
                     uint32_t t[16];
-                    tmem_ld16(tmem_base + lane_base + pend_buf * (kP * kN) + pl * kN + 16 * h, t);
+                    tmem_ld16(tmem_base + lane_base + pend_buf * (kP * kPS) + pl * kPS + 16 * h, t);
                     tmem_ld_wait();
 #pragma unroll
                     for (uint32_t n = 0; n < 16; ++n) S[n] += (int)t[n] >> pl;      // exact: plane sums are multiples of 2^pl
                 }
+                // q = d0 + 2^8 d1 + 2^16 d2 + 2^24 d3 summed per digit; |S| < 2^24 per job, so the conversions are exact
+                const int w = h < 2 ? 4 : 2;      // columns in this group
 #pragma unroll
-                for (int cc = 0; cc < 5; ++cc) {
-                    // q = d0 + 256 d1 + 65536 d2 summed per digit; |S| < 2^24 per job, so the conversions are exact
-                    const int c = 5 * (int)h + cc;
-                    const float t = fmaf((float)S[10 + cc], 65536.0f, fmaf((float)S[5 + cc], 256.0f, (float)S[cc]));
-                    v[c] = c < p.b ? t * s_scale[c] : 0.0f;
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c = 4 * (int)h + cc;
+                    if (cc < w) {
+                        const float t = fmaf((float)S[3 * w + cc], 16777216.0f,
+                                             fmaf((float)S[2 * w + cc], 65536.0f, fmaf((float)S[w + cc], 256.0f, (float)S[cc])));
+                        v[c] = c < p.b ? t * s_scale[c] : 0.0f;
+                    }
                 }
             }
             tc_fence_before();
@@ -325,7 +333,7 @@ spmm_head_i8_kernel(const __grid_constant__ CUtensorMap map_b, const Head8Params
             const uint32_t sl = job / p.num_mtiles, mtile = job % p.num_mtiles;
             const uint32_t c0 = (uint32_t)((uint64_t)p.NSC * sl / p.nslabs), c1 = (uint32_t)((uint64_t)p.NSC * (sl + 1) / p.nslabs);
             for (uint32_t sc = c0; sc < c1; ++sc) {
-                if ((a & (kG - 1)) == grp) {
+                if ((tn & (kG - 1)) == grp) {
                     mbar_wait2(&full[stage], phase, &a_empty[a], aphase ^ 1, 0x34 + grp, job, sc);
                     if (tracer) HEAD8_TRACE(3, tn);
                     const uint4 *bt = reinterpret_cast<const uint4 *>(ring + (size_t)stage * stage_bytes + bits_off) + trow * 2;
@@ -384,9 +392,9 @@ spmm_head_i8_kernel(const __grid_constant__ CUtensorMap map_b, const Head8Params
 CUtensorMap make_digit_map(const int8_t *base, uint64_t kpad)
 {
     CUtensorMap m;
-    const cuuint64_t gdim[2] = {kpad, kN};
+    const cuuint64_t gdim[2] = {kpad, (cuuint64_t)kHead8Rows};
     const cuuint64_t gstride[1] = {kpad};
-    const cuuint32_t box[2] = {128, kN};
+    const cuuint32_t box[2] = {128, (cuuint32_t)kHead8Rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(base), gdim, gstride, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -415,7 +423,11 @@ void spmm_head_i8_launch(Ctx &c, int b, const uint4 *bits, uint32_t num_mtiles, 
     p.slab = std::min<uint32_t>(NSC, (uint32_t)std::max(0, std::min(16, c.opt("spmm_head8_slab", 0))));
     p.nslabs = p.slab ? (NSC + p.slab - 1) / p.slab : std::max<uint32_t>(std::max<uint32_t>(1, std::min(nsplit, NSC)), (NSC + 255) / 256);
     p.b = b;
-    p.stages = (uint32_t)std::max(2, std::min(16, c.opt("spmm_head8_stages", 4)));
+    // ring length: a multiple of the group count, so that a ring stage is always consumed by the same worker group (a
+    // parity wait cannot tell "phase n done" from "phase n - 2 done"; a group must see every phase of the barriers it
+    // waits on).  4 stages x 14 KB stay under the 64 KB shared-memory carve-out, which leaves the L1 the tail gather
+    // that shares the SM lives on.
+    p.stages = (uint32_t)std::max(2, std::min(16, c.opt("spmm_head8_stages", 4))) & ~(kG - 1);
     // rows receive several partial sums (K cut into slabs): added into a zeroed output
     p.atomic = (p.nslabs > 1 || force_atomic) ? 1u : 0u;
     if (p.atomic && zero_out) ISLE_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)num_mtiles * kHeadTile * 16 * sizeof(float), stream));
@@ -429,6 +441,7 @@ void spmm_head_i8_launch(Ctx &c, int b, const uint4 *bits, uint32_t num_mtiles, 
         }
     }
     const CUtensorMap map = make_digit_map(digits, (uint64_t)NSC * 256);
+    static_assert(kBoxBytes % 1024 == 0 && (2 * kBoxBytes + kBitBytes) % 1024 == 0, "swizzled tiles must stay 1024-byte aligned");
     const uint32_t njobs = p.num_mtiles * p.nslabs;
     const unsigned grid = std::min<uint32_t>(njobs, (uint32_t)c.num_sms);
     // debugging aid: ISLE_HEAD8_TRACE=<file> dumps clock stamps of CTA 0's first super-chunks (synchronises)

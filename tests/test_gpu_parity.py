@@ -204,7 +204,7 @@ def test_spsptr_multiply_c1_split_rows(ctx, golden_c1, corpus_c1):
 ENGINE_OPTS = [
     dict(spmm_head=1, spmm_bfp=1, spmm_fork=0, spmm_head_i8=0),
     dict(spmm_head=1, spmm_bfp=1, spmm_fork=1, spmm_head_i8=0, spmm_head_density_ppm=1000, spmm_head_max=4096, spmm_head_seg=2),
-    dict(spmm_head=1, spmm_bfp=1, spmm_fork=1, spmm_head_density_ppm=1000, spmm_head_max=8192, spmm_head8_slab=1, spmm_head8_stages=3),
+    dict(spmm_head=1, spmm_bfp=1, spmm_fork=1, spmm_head_density_ppm=1000, spmm_head_max=8192, spmm_head8_slab=1, spmm_head8_stages=2),
     dict(spmm_head=0, spmm_bfp=0, spmm_fork=0),
     dict(spmm_head=0, spmm_bfp=1, spmm_fork=0),
     dict(spmm_head=1, spmm_bfp=0, spmm_fork=0),
@@ -214,7 +214,7 @@ ENGINE_OPTS = [
     dict(spmm_head=1, spmm_bfp=1, spmm_fork=1, spmm_head_density_ppm=1000, spmm_head_max=4096, spmm_head_seg=2),
 ]
 ENGINE_DEFAULTS = dict(spmm_head=1, spmm_bfp=1, spmm_fork=1, spmm_head_density_ppm=12000, spmm_head_max=4096,
-                       spmm_head_seg=16, spmm_head_i8=1, spmm_head8_slab=8, spmm_head8_stages=8)
+                       spmm_head_seg=16, spmm_head_i8=1, spmm_head8_slab=0, spmm_head8_stages=4)
 
 
 @pytest.mark.parametrize("opts", ENGINE_OPTS, ids=lambda o: "-".join(f"{k[5:]}{v}" for k, v in o.items()))
