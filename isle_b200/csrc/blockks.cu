@@ -31,14 +31,47 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
     return x ^ (x >> 31);
 }
 
-// arma::randu analogue (restarted_block_ks.h:212): uniform [0,1) floats, counter based.
-__global__ void randu_kernel(float *__restrict__ out, size_t n, uint64_t seed, uint64_t stream_id)
+// arma::randu analogue (restarted_block_ks.h:212): uniform [0,1) floats, counter based.  Fills rows [r0, r0 + nl) of
+// a global ng x cols column-major matrix into a local nl x cols one (ld nl): every rank of a row-sharded basis draws
+// its slice of the same matrix a single GPU would draw.
+__global__ void randu_kernel(float *__restrict__ out, size_t nl, size_t ng, size_t r0, int cols, uint64_t seed, uint64_t stream_id)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        const uint64_t h = splitmix64(seed ^ splitmix64(stream_id * 0x100000001B3ull + i));
+    for (; i < nl * (size_t)cols; i += stride) {
+        const size_t r = i % nl, cc = i / nl;
+        const uint64_t h = splitmix64(seed ^ splitmix64(stream_id * 0x100000001B3ull + (r0 + r) + cc * ng));
         out[i] = (float)(h >> 40) * (1.0f / 16777216.0f);
+    }
+}
+
+// loc(nl x cols, ld nl) = rows [r0, r0 + nl) of full(ng x cols, ld ng)
+__global__ void slice_rows_kernel(const float *__restrict__ full, size_t ng, size_t r0, size_t nl, int cols, float *__restrict__ loc)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < nl * (size_t)cols; i += stride) loc[i] = full[r0 + i % nl + (i / nl) * ng];
+}
+
+// full(ng x cols, ld ng) <- the ranks' row slices, gathered as [rank][cols][base] (rank g holds rows [g base, ...))
+__global__ void place_rows_kernel(const float *__restrict__ gathered, size_t ng, size_t base, int world, int cols, float *__restrict__ full)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < ng * (size_t)cols; i += stride) {
+        const size_t r = i % ng, cc = i / ng, g = r / base;
+        full[i] = gathered[(g * cols + cc) * base + (r - g * base)];
+    }
+}
+
+// pad(base x cols) <- loc(nl x cols, ld nl), zero rows beyond nl
+__global__ void pad_rows_kernel(const float *__restrict__ loc, size_t nl, size_t base, int cols, float *__restrict__ pad)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < base * (size_t)cols; i += stride) {
+        const size_t r = i % base, cc = i / base;
+        pad[i] = r < nl ? loc[r + cc * nl] : 0.0f;
     }
 }
 
@@ -312,24 +345,30 @@ __device__ __forceinline__ void gram_partial(const CholQrParams &p, const double
     __syncthreads();
 }
 
-// Every block: G = sum of partials (fixed order), Cholesky R (upper), Rinv = R^-1.  Returns
+// fixed-order sum of nb per-block partial Gram matrices (thread t < 256 owns entry t); the loads are independent of the
+// running sum, so unrolling keeps eight in flight
+__device__ __forceinline__ double sum_partials(const double *part, unsigned nb)
+{
+    double v = 0.0;
+    unsigned blk = 0;
+    for (; blk + 8 <= nb; blk += 8) {
+        double t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = part[(size_t)(blk + u) * 256 + threadIdx.x];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v += t[u];
+    }
+    for (; blk < nb; ++blk) v += part[(size_t)blk * 256 + threadIdx.x];
+    return v;
+}
+
+// Every block: G = sum of partials (fixed order) or the given Gram matrix, Cholesky R (upper), Rinv = R^-1.  Returns
 // false when a pivot is not safely positive.
 __device__ __forceinline__ bool chol_and_invert(const double *part, int b, double *G, double (*R)[kMaxB],
-                                                double (*Rinv)[kMaxB], int *s_ok, bool apply_rank_cut)
+                                                double (*Rinv)[kMaxB], int *s_ok, bool apply_rank_cut, bool part_is_G = false)
 {
-    {   // fixed-order sum; the loads are independent of the running sum, so unrolling keeps eight in flight
-        double v = 0.0;
-        const unsigned nb = gridDim.x;
-        unsigned blk = 0;
-        for (; blk + 8 <= nb; blk += 8) {
-            double t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = part[(size_t)(blk + u) * 256 + threadIdx.x];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v += t[u];
-        }
-        for (; blk < nb; ++blk) v += part[(size_t)blk * 256 + threadIdx.x];
-        G[threadIdx.x] = v;
+    {
+        G[threadIdx.x] = part_is_G ? part[threadIdx.x] : sum_partials(part, gridDim.x);
         R[threadIdx.x >> 4][threadIdx.x & 15] = 0.0;
         Rinv[threadIdx.x >> 4][threadIdx.x & 15] = 0.0;
         if (threadIdx.x == 0) *s_ok = 1;
@@ -404,6 +443,78 @@ cholqr2_kernel(CholQrParams p)
     }
     __syncthreads();
     // Q = F T: same 64-row tiles, coalesced loads and stores (thread = row of the tile, four columns each)
+    const int lrow = threadIdx.x & (kCholTile - 1), lcg = threadIdx.x >> 6;
+    for (int64_t row0 = (int64_t)blockIdx.x * kCholTile; row0 < p.n; row0 += (int64_t)gridDim.x * kCholTile) {
+        const int64_t row = row0 + lrow;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int col = lcg + 4 * u;
+            xs[lrow][col] = (row < p.n && col < b) ? (double)p.F[row + (size_t)col * p.n] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int col = lcg + 4 * u;
+            if (row < p.n && col < b) {
+                double y = 0.0;
+                for (int i = 0; i <= col; ++i) y += xs[lrow][i] * T[i][col];
+                p.Q[row + (size_t)col * p.n] = (float)y;
+            }
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.rank_out = b;
+}
+
+// ---- the same for a row-sharded block (SURVEY 8e option B): every rank holds rows [r0, r1) of F, the two Gram
+// matrices are all-reduced (256 doubles), every rank factorises them identically and writes its rows of Q.
+//   gram_rows_kernel (T = identity) -> sum -> all-reduce G1 -> gram_rows_kernel (T = R1^-1) -> sum -> all-reduce G2 ->
+//   cholqr2_finish_kernel.  A bad pivot in either factorisation makes finish report rank -1 (every rank alike).
+__global__ void __launch_bounds__(256)
+gram_rows_kernel(CholQrParams p, const double *__restrict__ G1 /* NULL: plain Gram of F */)
+{
+    __shared__ double xs[kCholTile][kMaxB + 1], ys[kCholTile][kMaxB + 1];
+    __shared__ double G[256];
+    __shared__ double R1[kMaxB][kMaxB], R1i[kMaxB][kMaxB];
+    __shared__ int s_ok;
+    extern __shared__ double red[];   // 16 x 256 doubles
+    if (G1) {
+        if (!chol_and_invert(G1, p.b, G, R1, R1i, &s_ok, true, true)) return;     // finish reports the failure
+        gram_partial(p, R1i, xs, ys, red, p.part);
+    } else {
+        gram_partial(p, nullptr, xs, ys, red, p.part);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const double *__restrict__ part, unsigned nb, double *__restrict__ G)
+{
+    G[threadIdx.x] = sum_partials(part, nb);
+}
+
+__global__ void __launch_bounds__(256)
+cholqr2_finish_kernel(CholQrParams p, const double *__restrict__ G1, const double *__restrict__ G2)
+{
+    __shared__ double xs[kCholTile][kMaxB + 1];
+    __shared__ double G[256];
+    __shared__ double R1[kMaxB][kMaxB], R1i[kMaxB][kMaxB], R2[kMaxB][kMaxB], R2i[kMaxB][kMaxB], T[kMaxB][kMaxB];
+    __shared__ int s_ok;
+    const int b = p.b;
+    bool ok = chol_and_invert(G1, b, G, R1, R1i, &s_ok, true, true);
+    __syncthreads();
+    ok = ok && chol_and_invert(G2, b, G, R2, R2i, &s_ok, false, true);
+    if (!ok) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *p.rank_out = -1;
+        return;
+    }
+    {
+        const int i = threadIdx.x >> 4, j = threadIdx.x & 15;
+        double t = 0.0, rr = 0.0;
+        for (int l = 0; l < kMaxB; ++l) { t += R1i[i][l] * R2i[l][j]; rr += R2[i][l] * R1[l][j]; }
+        T[i][j] = t;
+        if (blockIdx.x == 0 && i < b && j < b) p.R[i + (size_t)j * b] = (float)rr;
+    }
+    __syncthreads();
     const int lrow = threadIdx.x & (kCholTile - 1), lcg = threadIdx.x >> 6;
     for (int64_t row0 = (int64_t)blockIdx.x * kCholTile; row0 < p.n; row0 += (int64_t)gridDim.x * kCholTile) {
         const int64_t row = row0 + lrow;
@@ -716,7 +827,17 @@ struct PanelSimt {
 
 struct KsState {
     Ctx &c;
-    int64_t n;
+    int64_t n;                 // rows of the basis THIS rank holds (= ng unless the basis is row-sharded)
+    int64_t ng;                // rows of the operator (vocabulary size)
+    // Row-sharded basis (SURVEY 8e option B, document-sharded contexts): rank g holds rows [g base, min(ng, (g+1) base))
+    // of V and F.  Panel products, QR Gram sums and the truncation GEMM then cost 1/world per rank; what travels per block
+    // step: the next block all-gathered for the operator (ng x b), the operator's all-reduce (as before), the rows x b
+    // Gram-Schmidt coefficients all-reduced per pass, two 16 x 16 Gram matrices.  H and every decision stay replicated
+    // and identical on all ranks (all-reduced inputs, deterministic kernels).
+    bool shard = false;
+    int64_t r0 = 0, base = 0;
+    DevBuf<float> Xfull, Zfull, Qfull, gpad, grecv, ctmp;
+    DevBuf<double> gram1, gram2;
     int k, b, ncv, m;
     DevBuf<float> V, H, F, C, Rb, Tm, Wev, S, theta, Vtmp, Htmp, pack, work;
     PanelSimt ps;
@@ -732,10 +853,26 @@ struct KsState {
     int H_rows = 0, H_cols = 0;
     uint64_t seed, rng_calls = 0;
 
-    KsState(Ctx &ctx, int k_, int b_, uint64_t seed_) : c(ctx), n((int64_t)ctx.V), k(k_), b(b_), ps(ctx), seed(seed_)
+    KsState(Ctx &ctx, int k_, int b_, uint64_t seed_) : c(ctx), n((int64_t)ctx.V), ng((int64_t)ctx.V), k(k_), b(b_), ps(ctx), seed(seed_)
     {
         ncv = 2 * k + b;
         m = ncv - b;
+        // option ks_row_shard: 1 on, 0 off, -1 (default) on when it pays: the extra small collectives (a gather, three
+        // coefficient all-reduces and two Gram all-reduces per block step) cost ~0.1 ms per step, which a basis that
+        // streams from HBM (>= 256 MB: k >= ~300 at a 100k vocabulary) repays many times and an L2-resident one does not
+        // (c2, k = 100, 2 GPUs: 53.4 ms per step sharded against 49 replicated)
+        const int rs = c.opt("ks_row_shard", -1);
+        const bool rs_on = rs > 0 || (rs < 0 && (double)ng * ncv * 4.0 >= 256e6);
+        if (c.world > 1 && rs_on && c.opt("ks_panel_tc", 1) != 0 && c.opt("ks_custom_orth", 1) != 0 &&
+            ng % 4 == 0 && b <= 16) {
+            base = ((ng + c.world - 1) / c.world + 3) / 4 * 4;
+            if ((int64_t)(c.world - 1) * base + 64 <= ng) {      // every rank gets a real slice
+                shard = true;
+                r0 = (int64_t)c.rank * base;
+                n = std::min(ng, r0 + base) - r0;
+            }
+        }
+        c.counters["ks_row_sharded"] = shard ? 1.0 : 0.0;
         V.alloc((size_t)n * ncv);
         H.alloc((size_t)ncv * ncv);
         F.alloc((size_t)n * b);
@@ -748,8 +885,15 @@ struct KsState {
         Vtmp.alloc((size_t)n * k);
         Htmp.alloc((size_t)ncv * k);
         pack.alloc((size_t)(b + 1) * k);
-        qa.alloc((size_t)n * b);
-        qq.alloc((size_t)n);
+        qa.alloc((size_t)ng * b);      // the rank-revealing fallback QR runs on the gathered block
+        qq.alloc((size_t)ng);
+        if (shard) {
+            Xfull.alloc((size_t)ng * b); Zfull.alloc((size_t)ng * b); Qfull.alloc((size_t)ng * b);
+            const int gc = std::max(b, 128);           // widest gather: blocks of b columns, U in chunks of 128
+            gpad.alloc((size_t)base * gc); grecv.alloc((size_t)base * gc * c.world);
+            ctmp.alloc((size_t)ncv * kMaxB);
+            gram1.alloc(256); gram2.alloc(256);
+        }
         drank.alloc(1);
         dinfo.alloc(1);
         ISLE_CUDA_CHECK(cudaMemsetAsync(V.p, 0, V.bytes(), c.stream));
@@ -760,11 +904,12 @@ struct KsState {
         int per_sm = 0;
         ISLE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mgs_qr64_kernel, 256, 0));
         ISLE_REQUIRE(per_sm >= 1, ISLE_ERR_CUDA, "mgs_qr64_kernel cannot be made resident");
-        int want = (int)((n + 255) / 256);
+        int want = (int)((ng + 255) / 256);
         qr_grid = std::max(1, std::min(want, c.num_sms));   // one CTA per SM at most
         qpart.alloc((size_t)2 * qr_grid * kMaxB);
         // CholeskyQR2 fast path: as many co-resident CTAs as the 16-row tiles can use
         ISLE_CUDA_CHECK(cudaFuncSetAttribute(cholqr2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholDynSmem));
+        ISLE_CUDA_CHECK(cudaFuncSetAttribute(gram_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholDynSmem));
         ISLE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cholqr2_kernel, 256, kCholDynSmem));
         ISLE_REQUIRE(per_sm >= 1, ISLE_ERR_CUDA, "cholqr2_kernel cannot be made resident");
         chol_grid = std::max(1, std::min((int)((n + kCholTile - 1) / kCholTile), c.num_sms));   // every CTA re-sums all partials: keep them few
@@ -775,7 +920,9 @@ struct KsState {
         ps.init(n, ncv, panel_v2);
         // tensor-core panel products (panel_tc.cu) once the basis has at least this many columns
         panel_tc = c.opt("ks_panel_tc", 1) != 0 && PanelTc::usable(n) && b <= 16;
-        panel_tc_min_rows = c.opt("ks_panel_tc_min_rows", 0);
+        panel_tc_min_rows = shard ? 0 : c.opt("ks_panel_tc_min_rows", 0);
+        ISLE_REQUIRE(!shard || panel_tc, ISLE_ERR_ARG, "block_ks: the row-sharded basis needs the tensor-core panel engine");
+        ptc.sharded = shard;
         if (panel_tc) ptc.init(c, n, ncv);
         gs_elide = c.opt("ks_gs_elide", 1) != 0;
         gs_passes = std::max(2, std::min(3, c.opt("ks_gs_passes", 3)));
@@ -786,8 +933,42 @@ struct KsState {
 
     void randu(float *dst, int cols)
     {
-        randu_kernel<<<grid_for((size_t)n * cols, 256), 256, 0, c.stream>>>(dst, (size_t)n * cols, seed, ++rng_calls);
+        randu_kernel<<<grid_for((size_t)n * cols, 256), 256, 0, c.stream>>>(dst, (size_t)n, (size_t)ng, (size_t)r0, cols, seed, ++rng_calls);
         count_launch(c);
+    }
+
+    // full(ng x cols, ld ng) <- all ranks' row slices loc(n x cols, ld n); cols <= max(b, 128)
+    void gather(const float *loc, int cols, float *full)
+    {
+        pad_rows_kernel<<<grid_for((size_t)base * cols, 256), 256, 0, c.stream>>>(loc, (size_t)n, (size_t)base, cols, gpad.p);
+        allgather_f32(c, gpad.p, grecv.p, (size_t)base * cols);
+        place_rows_kernel<<<grid_for((size_t)ng * cols, 256), 256, 0, c.stream>>>(grecv.p, (size_t)ng, (size_t)base, c.world, cols, full);
+        count_launch(c, 2);
+    }
+    void slice(const float *full, int cols, float *loc)
+    {
+        slice_rows_kernel<<<grid_for((size_t)n * cols, 256), 256, 0, c.stream>>>(full, (size_t)ng, (size_t)r0, (size_t)n, cols, loc);
+        count_launch(c);
+    }
+
+    // Rank-revealing fallback for a row-sharded block: gather it, run the reference's MGS on the whole block on every rank
+    // (deterministic kernel, identical result), keep this rank's rows of Q.
+    int qr_gathered(const float *Fsrc, int cols, float *Qdst)
+    {
+        gather(Fsrc, cols, Xfull.p);
+        ISLE_CUDA_CHECK(cudaMemsetAsync(Qfull.p, 0, (size_t)ng * cols * 4, c.stream));
+        ISLE_CUDA_CHECK(cudaMemsetAsync(Rb.p, 0, Rb.bytes(), c.stream));
+        QrParams p;
+        p.F = Xfull.p; p.n = ng; p.b = cols; p.a = qa.p; p.q = qq.p; p.Q = Qfull.p; p.R = Rb.p;
+        p.rank_out = drank.p; p.part = qpart.p;
+        void *args[] = {&p};
+        ISLE_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)mgs_qr64_kernel, dim3(qr_grid), dim3(256), args, 0, c.stream));
+        count_launch(c);
+        slice(Qfull.p, cols, Qdst);
+        int rank = -1;
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(&rank, drank.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        return rank;
     }
 
     // [Q,R] = mgs_qr64(Fsrc); Q -> Qdst (ld n); R -> Rb (b x b, zero padded).  Returns rank.
@@ -796,6 +977,25 @@ struct KsState {
         ISLE_CUDA_CHECK(cudaMemsetAsync(Rb.p, 0, Rb.bytes(), c.stream));
         StatScope s(c, "ks_qr");
         int rank = -1;
+        if (shard) {
+            if (fast_qr) {
+                CholQrParams q;
+                q.F = Fsrc; q.n = n; q.b = cols; q.Q = Qdst; q.R = Rb.p; q.rank_out = drank.p; q.part = cpart.p;
+                gram_rows_kernel<<<chol_grid, 256, kCholDynSmem, c.stream>>>(q, nullptr);
+                sum_partials_kernel<<<1, 256, 0, c.stream>>>(cpart.p, (unsigned)chol_grid, gram1.p);
+                allreduce_sum_f64(c, gram1.p, 256);
+                gram_rows_kernel<<<chol_grid, 256, kCholDynSmem, c.stream>>>(q, gram1.p);
+                sum_partials_kernel<<<1, 256, 0, c.stream>>>(cpart.p, (unsigned)chol_grid, gram2.p);
+                allreduce_sum_f64(c, gram2.p, 256);
+                cholqr2_finish_kernel<<<chol_grid, 256, 0, c.stream>>>(q, gram1.p, gram2.p);
+                count_launch(c, 5);
+                ISLE_CUDA_CHECK(cudaMemcpyAsync(&rank, drank.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+                ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+                if (rank >= 0) return rank;
+                c.counters["ks_qr_fallbacks"] += 1.0;
+            }
+            return qr_gathered(Fsrc, cols, Qdst);
+        }
         if (fast_qr) {
             CholQrParams q;
             q.F = Fsrc; q.n = n; q.b = cols; q.Q = Qdst; q.R = Rb.p; q.rank_out = drank.p; q.part = cpart.p;
@@ -822,8 +1022,17 @@ struct KsState {
     // NOTE: for cols < b the R rows use leading dimension `cols`; callers that need R pass cols == b.
 
     void gemm_tn(int rows, int cols, const float *A, const float *Bm, float *Cm, int ldc)
-    {   // Cm(rows x cols) = A(n x rows)^T Bm(n x cols)
+    {   // Cm(rows x cols) = A(n x rows)^T Bm(n x cols); summed over the ranks' row slices when the basis is sharded
         const float one = 1.f, zero = 0.f;
+        if (shard) {
+            ISLE_CUBLAS_CHECK(cublasSgemm(c.cublas, CUBLAS_OP_T, CUBLAS_OP_N, rows, cols, (int)n, &one, A, (int)n, Bm,
+                                          (int)n, &zero, ctmp.p, rows));
+            allreduce_sum_f32(c, ctmp.p, (size_t)rows * cols);
+            ISLE_CUDA_CHECK(cudaMemcpy2DAsync(Cm, (size_t)ldc * 4, ctmp.p, (size_t)rows * 4, (size_t)rows * 4, cols,
+                                              cudaMemcpyDeviceToDevice, c.stream));
+            count_launch(c);
+            return;
+        }
         ISLE_CUBLAS_CHECK(cublasSgemm(c.cublas, CUBLAS_OP_T, CUBLAS_OP_N, rows, cols, (int)n, &one, A, (int)n, Bm,
                                       (int)n, &zero, Cm, ldc));
         count_launch(c);
@@ -858,7 +1067,26 @@ struct KsState {
     void op(const float *X, float *Z)
     {
         StatScope s(c, "ks_op");
+        if (shard) {     // the operator works on whole vectors: gather the block, apply (all-reduce inside), keep my rows
+            gather(X, b, Xfull.p);
+            spsptr_multiply_dev(c, b, Xfull.p, Zfull.p);
+            slice(Zfull.p, b, Z);
+            return;
+        }
         spsptr_multiply_dev(c, b, X, Z);
+    }
+
+    // U(ng x k, column-major) <- the first k columns of the (possibly row-sharded) basis
+    void export_U(float *U)
+    {
+        if (!shard) {
+            ISLE_CUDA_CHECK(cudaMemcpyAsync(U, V.p, (size_t)ng * k * 4, cudaMemcpyDeviceToDevice, c.stream));
+            return;
+        }
+        for (int j0 = 0; j0 < k; j0 += 128) {
+            const int w = std::min(128, k - j0);
+            gather(Vcol(j0), w, U + (size_t)j0 * ng);
+        }
     }
 
     // restarted_block_ks.h:204-259
@@ -1058,7 +1286,7 @@ void block_ks(Ctx &c, uint64_t k64, int b, int max_restarts, float tol, uint64_t
     if (evalues_out) std::copy(evs.begin(), evs.begin() + k, evalues_out);
     c.k = k64;
     c.U.alloc((size_t)c.V * k);
-    ISLE_CUDA_CHECK(cudaMemcpyAsync(c.U.p, ks.V.p, (size_t)c.V * k * 4, cudaMemcpyDeviceToDevice, c.stream));
+    ks.export_U(c.U.p);
     if (U_out)
         ISLE_CUDA_CHECK(cudaMemcpyAsync(U_out, c.U.p, (size_t)c.V * k * 4, cudaMemcpyDeviceToHost, c.stream));
     ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));

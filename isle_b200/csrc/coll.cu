@@ -45,6 +45,16 @@ void bcast_f32(Ctx &c, float *buf, size_t n, int root)
     if (c.world <= 1 || n == 0) return;
     ISLE_NCCL_CHECK(ncclBroadcast(buf, buf, n, ncclFloat32, root, c.comm, c.stream));
 }
+void allgather_f32(Ctx &c, const float *send, float *recv, size_t count)
+{
+    if (count == 0) return;
+    if (c.world <= 1) {
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(recv, send, count * 4, cudaMemcpyDeviceToDevice, c.stream));
+        return;
+    }
+    StatScope s(c, "allgather");
+    ISLE_NCCL_CHECK(ncclAllGather(send, recv, count, ncclFloat32, c.comm, c.stream));
+}
 #else
 static void need_nccl(Ctx &c)
 {
@@ -66,6 +76,11 @@ void allgather_f64(Ctx &c, const double *send, double *recv)
     ISLE_CUDA_CHECK(cudaMemcpyAsync(recv, send, 8, cudaMemcpyDeviceToDevice, c.stream));
 }
 void bcast_f32(Ctx &c, float *, size_t, int) { need_nccl(c); }
+void allgather_f32(Ctx &c, const float *send, float *recv, size_t count)
+{
+    need_nccl(c);
+    ISLE_CUDA_CHECK(cudaMemcpyAsync(recv, send, count * 4, cudaMemcpyDeviceToDevice, c.stream));
+}
 #endif
 
 }  // namespace isle

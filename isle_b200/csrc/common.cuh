@@ -369,6 +369,8 @@ struct PanelTc {
     DevBuf<float> csplit;              // [32][cpitch]: hi / lo of the coefficient block C
     DevBuf<float> part;                // partial results [segments][m][16]
     DevBuf<uint32_t> flags;            // largest |coefficient| of pass 0 / 1 (bit patterns), skip flag, elided-pass counter
+    bool sharded = false;              // n = this rank's rows of a row-sharded basis: W^T F is all-reduced over the ranks
+    DevBuf<float> packed;              // [ncv][16] coefficients on their way through the all-reduce
     void init(Ctx &c, int64_t n, int ncv);
     static bool usable(int64_t n);
     void begin_step(Ctx &c);
@@ -424,5 +426,6 @@ void allreduce_max_u32(Ctx &c, uint32_t *buf, size_t n);
 void allgather_u64(Ctx &c, const unsigned long long *send, unsigned long long *recv);  // 1 per rank
 void allgather_f64(Ctx &c, const double *send, double *recv);                         // 1 per rank
 void bcast_f32(Ctx &c, float *buf, size_t n, int root);
+void allgather_f32(Ctx &c, const float *send, float *recv, size_t count);   // `count` floats per rank
 
 }  // namespace isle

@@ -383,6 +383,45 @@ wtf_reduce_tc_kernel(const float *__restrict__ partial, int nseg, int rows, int 
     }
 }
 
+// Row-sharded basis (SURVEY 8e option B): every rank holds rows [r0, r1) of W and F, so W^T F is a sum over ranks.
+// pack: packed[j * 16 + c] = this rank's sum over its segments (same fixed order as above); after the all-reduce,
+// finalize writes C, Hk, csplit and the pass maximum from the global coefficients (identical on every rank).
+__global__ void __launch_bounds__(256)
+wtf_pack_tc_kernel(const float *__restrict__ partial, int nseg, int rows, int b, float *__restrict__ packed,
+                   const uint32_t *__restrict__ skip)
+{
+    if (skip && *skip) return;
+    const int lane = threadIdx.x & 31;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= rows * 16) return;
+    const int j = t >> 4, c = t & 15;
+    float v = 0.f;
+    if (c < b)
+        for (int s = lane; s < nseg; s += 32) v += partial[((size_t)s * rows + j) * 16 + c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) packed[t] = v;
+}
+
+__global__ void __launch_bounds__(256)
+wtf_finalize_tc_kernel(const float *__restrict__ packed, int rows, int b, float *__restrict__ C, int ldc, float *__restrict__ Hk,
+                       int ldh, int hk_assign, float *__restrict__ csplit, size_t cpitch, uint32_t *__restrict__ cmax_bits,
+                       const uint32_t *__restrict__ skip)
+{
+    if (skip && *skip) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * 16) return;
+    const int j = t >> 4, c = t & 15;
+    if (c >= b) return;
+    const float v = packed[t];
+    C[j + (size_t)c * ldc] = v;
+    if (Hk) Hk[j + (size_t)c * ldh] = hk_assign ? v : Hk[j + (size_t)c * ldh] + v;
+    const float hi = __uint_as_float(tf32_rna(v));
+    csplit[(size_t)c * cpitch + j] = hi;
+    csplit[(size_t)(16 + c) * cpitch + j] = v - hi;
+    if (cmax_bits) atomicMax(cmax_bits, __float_as_uint(fabsf(v)) & 0x7FFFFFFFu);
+}
+
 // skip = 1 when the pass just finished only moved coefficients below `ratio` of the first pass's (they are then
 // below fp32 resolution of H and a further pass cannot improve the orthogonality); counts the elisions
 __global__ void gs_decide_kernel(const uint32_t *__restrict__ cmax_bits, float ratio, uint32_t *__restrict__ skip,
@@ -460,6 +499,10 @@ void PanelTc::init(Ctx &c, int64_t n_, int ncv_)
     part.alloc(std::max(nseg_w * (size_t)ncv, nseg_f * (size_t)n) * 16);
     flags.alloc(4);        // [0], [1]: largest |coefficient| of the first / the latest pass; [2]: skip flag; [3]: elided passes
     ISLE_CUDA_CHECK(cudaMemsetAsync(flags.p, 0, flags.bytes(), c.stream));
+    if (sharded) {
+        packed.alloc((size_t)ncv * 16);
+        ISLE_CUDA_CHECK(cudaMemsetAsync(packed.p, 0, packed.bytes(), c.stream));
+    }
 }
 
 // Start of a block step: no pass elided yet.
@@ -516,9 +559,20 @@ void PanelTc::wtf(Ctx &c, const float *W, int rows, int b, float *C, int ldc, fl
         StatScope s(c, "ks_wtfred", (double)p.nseg * rows * 64.0);
         // stale csplit columns of an earlier, wider call cannot matter: the W tile is zero beyond `rows`
         // and csplit only ever holds finite values
-        wtf_reduce_tc_kernel<<<(unsigned)(((size_t)rows * 16 * 32 + 255) / 256), 256, 0, c.stream>>>(
-            part.p, (int)p.nseg, rows, b, C, ldc, Hk, ldh, assign ? 1 : 0, csplit.p, cpitch, cmax, p.skip);
-        count_launch(c);
+        if (sharded) {
+            // the basis is row-sharded: the coefficients are a sum over ranks.  An elided pass still takes part in
+            // the collective (every rank took the same decision and left `packed` alone: the sum is never read).
+            wtf_pack_tc_kernel<<<(unsigned)(((size_t)rows * 16 * 32 + 255) / 256), 256, 0, c.stream>>>(part.p, (int)p.nseg, rows, b,
+                                                                                                       packed.p, p.skip);
+            allreduce_sum_f32(c, packed.p, (size_t)rows * 16);
+            wtf_finalize_tc_kernel<<<(unsigned)(((size_t)rows * 16 + 255) / 256), 256, 0, c.stream>>>(
+                packed.p, rows, b, C, ldc, Hk, ldh, assign ? 1 : 0, csplit.p, cpitch, cmax, p.skip);
+            count_launch(c, 2);
+        } else {
+            wtf_reduce_tc_kernel<<<(unsigned)(((size_t)rows * 16 * 32 + 255) / 256), 256, 0, c.stream>>>(
+                part.p, (int)p.nseg, rows, b, C, ldc, Hk, ldh, assign ? 1 : 0, csplit.p, cpitch, cmax, p.skip);
+            count_launch(c);
+        }
     }
 }
 

@@ -34,6 +34,7 @@ def stages(ctx, V, D, k, vals, rows, offsets, avg, nz, centers0=None, U_override
     B.threshold_and_copy(A, z, nn)
     bv, br, bo, oc = B.download()
     ev, U = B.compute_block_ks(k, seed=seed, want_U=True)
+    row_sharded = ctx.stat("ks_row_sharded")
     if U_override is not None:      # identical projection for the k-means comparison
         B.set_U(U_override)
     seeds, coords, res = B.kmeans_init_on_projected_space(k, 1, seed=seed)
@@ -47,7 +48,7 @@ def stages(ctx, V, D, k, vals, rows, offsets, avg, nz, centers0=None, U_override
     full_in = full.copy()
     B.cleanup_after_eigensolver()
     B.run_lloyds(k, full, None, 10)
-    return dict(z=z, nn=nn, bv=bv, br=br, bo=bo, oc=oc, ev=ev, U=U, seeds=seeds, coords=coords, centers=c0,
+    return dict(row_sharded=row_sharded, z=z, nn=nn, bv=bv, br=br, bo=bo, oc=oc, ev=ev, U=U, seeds=seeds, coords=coords, centers=c0,
                 obj=B.last_lloyd["objective"], assign=B.last_lloyd["assign"], iters=B.last_lloyd["iters"],
                 full_in=full_in, full=full, full_obj=B.last_lloyd_full["objective"], full_assign=B.last_lloyd_full["assign"],
                 full_iters=B.last_lloyd_full["iters"])
@@ -70,6 +71,9 @@ def main():
     nz_local = int((np.diff(lo) > 0).sum())
 
     sh = _capi.Context(local, rank, world, bytes(idt.cpu().numpy().tobytes()))
+    # the check covers the row-sharded Krylov basis unless told otherwise (the library's default switches it on only for
+    # bases that stream from HBM)
+    sh.set_option("ks_row_shard", 0 if os.environ.get("ISLE_KS_ROW_SHARD") == "0" else 1)
     r = stages(sh, c.V, d1 - d0, c.k, vals[e0:e1], c.rows[e0:e1], lo, float(avg), nz_local)
     # the single-GPU run; its k-means stages get the sharded run's U and k-means++ centers so that
     # both Lloyd runs see the same projection and start identically
@@ -98,11 +102,21 @@ def main():
         b0, b1 = int(s["bo"][sel[0]]), int(s["bo"][sel[-1] + 1])
         check(np.array_equal(s["br"][b0:b1], r["br"]) and np.array_equal(s["bv"][b0:b1], r["bv"]) and
               np.array_equal(s["bo"][sel[0]:sel[-1] + 2] - b0, r["bo"]), "B slice differs")
+    # the Krylov basis of the sharded run is row-sharded over the vocabulary (SURVEY 8e option B) unless switched off
+    want_rs = 0.0 if os.environ.get("ISLE_KS_ROW_SHARD") == "0" else 1.0
+    check(r["row_sharded"] == want_rs and s["row_sharded"] == 0.0, f"row sharding flag {r['row_sharded']} / {s['row_sharded']}")
     sv_r, sv_s = np.sqrt(r["ev"]), np.sqrt(s["ev"])
     rel = float(np.max(np.abs(sv_r - sv_s) / sv_s))
     check(rel < 1e-4, f"singular values differ: {rel:.2e}")
     ang = O.principal_angle_sin(r["U"], s["U"])
-    check(ang < 1e-3, f"principal angle {ang:.2e}")
+    if name == "c3m":
+        # the k-th eigenvalue of c3m is 0.46 % above the next: a solver stopping at residual 1e-4 pins span(U) only to
+        # ~tol / gap = 2e-2 (tests/test_gpu_largek.py); the well-separated leading 300 Ritz vectors must agree to 1e-3
+        U1, U2 = r["U"].astype(np.float64), s["U"].astype(np.float64)
+        lead = float(np.linalg.norm(U1[:, :300] - U2 @ (U2.T @ U1[:, :300]), 2))
+        check(lead < 1e-3 and ang < 1e-2, f"principal angle {ang:.2e}, leading 300 vectors {lead:.2e}")
+    else:
+        check(ang < 1e-3, f"principal angle {ang:.2e}")
     # Lloyd: the sharded run used its own seeds; re-run it from the same centers as `s`
     # (already the case: s started from r's coords).  Compare objective and local assignments.
     obj_rel = abs(r["obj"] - s["obj"]) / s["obj"]
