@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "seg_select.cuh"
 
 namespace isle {
 
@@ -111,6 +112,49 @@ cw_pick_kernel(const float *__restrict__ sorted, const int64_t *__restrict__ seg
     thresholds[seg_key[s]] = sorted[b + (n > (int64_t)r ? (int64_t)r - 1 : n - 1)];
 }
 
+// ---- document-sharded form: the candidates' values stay where their documents are; four radix rounds of
+// (local histogram over the rank's documents, allreduce, pick) find every segment's threshold exactly
+__global__ void __launch_bounds__(256)
+cw_hist_docs_kernel(const float *__restrict__ a_val, const uint32_t *__restrict__ a_row, const int64_t *__restrict__ a_off,
+                    const uint32_t *__restrict__ doc_ids, const uint32_t *__restrict__ cl_ids, uint32_t ndocs, uint32_t V,
+                    const uint32_t *__restrict__ flag, const uint32_t *__restrict__ slot, const uint32_t *__restrict__ prefix, int round,
+                    uint32_t *__restrict__ hist)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (; i < ndocs; i += nw) {
+        const uint32_t d = doc_ids ? doc_ids[i] : i;
+        const uint32_t cl = cl_ids ? cl_ids[i] : 0u;
+        if (cl == kNoCluster) continue;
+        for (int64_t p = a_off[d] + lane, e = a_off[d + 1]; p < e; p += 32) {
+            const size_t key = (size_t)cl * V + a_row[p];
+            if (!flag[key]) continue;
+            const uint32_t s = slot[key], o = segsel::ordered(a_val[p]);
+            if (segsel::matches(o, prefix[s], round)) atomicAdd(hist + (size_t)s * 256 + ((o >> (24 - 8 * round)) & 255u), 1u);
+        }
+    }
+}
+
+// kth[slot] = 0-based rank from the top of the value wanted from the segment (:508-520); seg_key[slot] = key
+__global__ void __launch_bounds__(256)
+cw_kth_kernel(const uint32_t *__restrict__ flag, const uint32_t *__restrict__ slot, const uint32_t *__restrict__ count, size_t nkeys,
+              uint32_t r, uint32_t *__restrict__ kth, uint32_t *__restrict__ seg_key)
+{
+    const size_t key = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= nkeys || !flag[key]) return;
+    const uint32_t s = slot[key], n = count[key];
+    kth[s] = n > r ? r - 1 : n - 1;
+    seg_key[s] = (uint32_t)key;
+}
+
+__global__ void __launch_bounds__(256)
+cw_result_kernel(const uint32_t *__restrict__ prefix, const uint32_t *__restrict__ seg_key, uint32_t nseg, float *__restrict__ thresholds)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nseg) thresholds[seg_key[s]] = segsel::unordered(prefix[s]);
+}
+
 struct U32ToI64 {
     __host__ __device__ int64_t operator()(uint32_t x) const { return (int64_t)x; }
 };
@@ -137,14 +181,11 @@ find_catchwords_kernel(const float *__restrict__ thr, uint32_t V, uint32_t k, do
 // thresholds (device, k x V, zeroed here) for the documents listed in doc_ids (NULL: all D documents) with clusters cl_ids
 void thresholds_device(Ctx &c, uint32_t k, uint32_t r, const uint32_t *doc_ids, const uint32_t *cl_ids, uint32_t ndocs, float *thr)
 {
-    // clusters span ranks when documents are sharded: the sharded form (allreduced counts + a gather of each candidate
-    // segment's values to one rank) is not built yet
-    ISLE_REQUIRE(c.world == 1, ISLE_ERR_ARG, "catchword thresholds: single-GPU contexts only for now");
     const uint32_t V = (uint32_t)c.V;
     const size_t nkeys = (size_t)k * V;
     ISLE_CUDA_CHECK(cudaMemsetAsync(thr, 0, nkeys * sizeof(float), c.stream));
     c.counters["cw_candidates"] = 0.0;
-    if (!ndocs) return;
+    if (!ndocs && c.world == 1) return;      // a sharded rank without documents still takes part in the collectives
     DevBuf<uint32_t> count(nkeys), cl_size(k), flag(nkeys), take(nkeys), slot(nkeys);
     DevBuf<int64_t> voff(nkeys + 1);
     ISLE_CUDA_CHECK(cudaMemsetAsync(count.p, 0, count.bytes(), c.stream));
@@ -152,8 +193,12 @@ void thresholds_device(Ctx &c, uint32_t k, uint32_t r, const uint32_t *doc_ids, 
     const unsigned wgrid = grid_for((size_t)ndocs * 32, 256, c.num_sms * 8);
     {
         StatScope s(c, "cw_count", (double)c.nnzA * 4.0);
-        cw_count_kernel<<<wgrid, 256, 0, c.stream>>>(c.a_val.p, c.a_row.p, c.a_off.p, doc_ids, cl_ids, ndocs, V, count.p, cl_size.p);
+        if (ndocs) cw_count_kernel<<<wgrid, 256, 0, c.stream>>>(c.a_val.p, c.a_row.p, c.a_off.p, doc_ids, cl_ids, ndocs, V, count.p, cl_size.p);
         count_launch(c);
+    }
+    if (c.world > 1) {      // clusters span ranks: counts and sizes are global from here on
+        allreduce_sum_u32(c, count.p, count.n);
+        allreduce_sum_u32(c, cl_size.p, cl_size.n);
     }
     cw_candidates_kernel<<<(unsigned)((nkeys + 255) / 256), 256, 0, c.stream>>>(count.p, cl_size.p, nkeys, V, r, flag.p, take.p);
     count_launch(c);
@@ -179,6 +224,28 @@ void thresholds_device(Ctx &c, uint32_t k, uint32_t r, const uint32_t *doc_ids, 
     const int64_t nvals = last_off + last_take;
     c.counters["cw_candidates"] = nseg;
     if (!nseg) return;
+    if (c.world > 1) {
+        // the values of a segment live on several ranks: exact distributed radix select (seg_select.cuh), no values travel
+        DevBuf<uint32_t> kth(nseg), prefix(nseg), skey(nseg), hist((size_t)nseg * 256);
+        ISLE_CUDA_CHECK(cudaMemsetAsync(prefix.p, 0, prefix.bytes(), c.stream));
+        cw_kth_kernel<<<(unsigned)((nkeys + 255) / 256), 256, 0, c.stream>>>(flag.p, slot.p, count.p, nkeys, r, kth.p, skey.p);
+        count_launch(c);
+        for (int round = 0; round < 4; ++round) {
+            ISLE_CUDA_CHECK(cudaMemsetAsync(hist.p, 0, hist.bytes(), c.stream));
+            if (ndocs) {
+                cw_hist_docs_kernel<<<wgrid, 256, 0, c.stream>>>(c.a_val.p, c.a_row.p, c.a_off.p, doc_ids, cl_ids, ndocs, V, flag.p, slot.p,
+                                                                 prefix.p, round, hist.p);
+                count_launch(c);
+            }
+            allreduce_sum_u32(c, hist.p, hist.n);
+            segsel::pick_kernel<<<(nseg + 127) / 128, 128, 0, c.stream>>>(hist.p, nseg, kth.p, prefix.p);
+            count_launch(c);
+        }
+        cw_result_kernel<<<(nseg + 255) / 256, 256, 0, c.stream>>>(prefix.p, skey.p, nseg, thr);
+        count_launch(c);
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        return;
+    }
     ISLE_REQUIRE(nvals < (int64_t)1 << 31, ISLE_ERR_RANGE, "catchword thresholds: more than 2^31 candidate values");
     DevBuf<int64_t> seg_begin(nseg), seg_end(nseg);
     DevBuf<uint32_t> seg_key(nseg);

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "seg_select.cuh"
 
 namespace isle {
 
@@ -119,6 +120,31 @@ __global__ void tm_threshold_kernel(const unsigned long long *__restrict__ sorte
     thr[t] = v;
 }
 
+// document-sharded thresholds: entries per topic (local), then the selection set-up from the global counts
+__global__ void __launch_bounds__(256)
+tm_topic_count_kernel(const uint32_t *__restrict__ e_topic, int64_t n, uint32_t *__restrict__ cnt)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) atomicAdd(cnt + e_topic[i], 1u);
+}
+
+__global__ void tm_kth_kernel(const uint32_t *__restrict__ gcount, const uint32_t *__restrict__ has_catch, uint32_t k, uint64_t rank,
+                              uint32_t *__restrict__ kth)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    kth[t] = (has_catch[t] && rank >= 1 && (uint64_t)gcount[t] >= rank) ? (uint32_t)(rank - 1) : 0xFFFFFFFFu;
+}
+
+__global__ void tm_thr_from_prefix_kernel(const uint32_t *__restrict__ prefix, const uint32_t *__restrict__ gcount,
+                                          const uint32_t *__restrict__ has_catch, uint32_t k, uint64_t rank, float *__restrict__ thr)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    thr[t] = (has_catch[t] && rank >= 1 && (uint64_t)gcount[t] >= rank) ? segsel::unordered(prefix[t]) : 0.0f;
+}
+
 __global__ void tm_has_catch_kernel(const int32_t *__restrict__ topic_of_word, uint32_t V, uint32_t k, uint32_t *__restrict__ has_catch)
 {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -191,7 +217,8 @@ void construct_topic_model(Ctx &c, uint64_t k64, const int32_t *topic_of_word_ho
 {
     ISLE_REQUIRE(c.a_off.p != nullptr && c.V > 0, ISLE_ERR_ARG, "construct_topic_model: upload_A first");
     ISLE_REQUIRE(k64 >= 1 && k64 <= 65536 && topic_of_word_host && cluster_of_doc_host, ISLE_ERR_ARG, "construct_topic_model: bad arguments");
-    ISLE_REQUIRE(c.world == 1, ISLE_ERR_ARG, "construct_topic_model: single-GPU contexts only for now");
+    // document-sharded: the catchword sums are local to the documents a rank holds; the per-topic thresholds come from an
+    // exact distributed radix select over all ranks' sums (seg_select.cuh); the local model contributions are allreduced
     const uint32_t k = (uint32_t)k64, V = (uint32_t)c.V, D = (uint32_t)c.D;
     StatScope total(c, "topic_model", (double)c.nnzA * 24.0 + (double)V * k * 8.0);
     DevBuf<int32_t> tw(V);
@@ -248,7 +275,26 @@ void construct_topic_model(Ctx &c, uint64_t k64, const int32_t *topic_of_word_ho
 
     // ---- model thresholds: rank-th largest sum per topic
     DevBuf<float> thr(k);
-    if (n > 0) {
+    if (c.world > 1) {
+        DevBuf<uint32_t> gcount(k), kth(k), prefix(k), hist((size_t)k * 256);
+        ISLE_CUDA_CHECK(cudaMemsetAsync(gcount.p, 0, gcount.bytes(), c.stream));
+        ISLE_CUDA_CHECK(cudaMemsetAsync(prefix.p, 0, prefix.bytes(), c.stream));
+        const unsigned egrid = grid_for((size_t)std::max<int64_t>(n, 1), 256, c.num_sms * 8);
+        if (n > 0) tm_topic_count_kernel<<<egrid, 256, 0, c.stream>>>(c.tm_topic.p, n, gcount.p);
+        allreduce_sum_u32(c, gcount.p, gcount.n);
+        tm_kth_kernel<<<(k + 127) / 128, 128, 0, c.stream>>>(gcount.p, has_catch.p, k, rank_threshold, kth.p);
+        count_launch(c, 2);
+        for (int round = 0; round < 4; ++round) {
+            ISLE_CUDA_CHECK(cudaMemsetAsync(hist.p, 0, hist.bytes(), c.stream));
+            if (n > 0) segsel::hist_pairs_kernel<<<egrid, 256, 0, c.stream>>>(c.tm_topic.p, c.tm_val.p, n, prefix.p, round, hist.p);
+            allreduce_sum_u32(c, hist.p, hist.n);
+            segsel::pick_kernel<<<(k + 127) / 128, 128, 0, c.stream>>>(hist.p, k, kth.p, prefix.p);
+            count_launch(c, 2);
+        }
+        tm_thr_from_prefix_kernel<<<(k + 127) / 128, 128, 0, c.stream>>>(prefix.p, gcount.p, has_catch.p, k, rank_threshold, thr.p);
+        count_launch(c);
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    } else if (n > 0) {
         DevBuf<unsigned long long> keys((size_t)n), sorted((size_t)n);
         tm_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(c.tm_topic.p, c.tm_val.p, n, keys.p);
         int topic_bits = 1;
@@ -278,6 +324,7 @@ void construct_topic_model(Ctx &c, uint64_t k64, const int32_t *topic_of_word_ho
                                                                                                k, c.tm_model.p);
         count_launch(c);
     }
+    if (c.world > 1) allreduce_sum_f32(c, c.tm_model.p, c.tm_model.n);
     tm_normalize_kernel<<<k, 256, 0, c.stream>>>(c.tm_model.p, V);
     count_launch(c);
     if (model_out)

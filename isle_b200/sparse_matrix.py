@@ -115,7 +115,8 @@ class SparseMatrix:
         return [np.nonzero(tw == t)[0] for t in range(int(num_topics))]
 
 
-    def construct_topic_model(self, num_topics: int, cluster_of_doc: np.ndarray, catchwords, want_pairs: bool = True):
+    def construct_topic_model(self, num_topics: int, cluster_of_doc: np.ndarray, catchwords, want_pairs: bool = True,
+                              total_docs: Optional[int] = None):
         """src/sparseMatrix.cpp:597-838.  ``cluster_of_doc`` uint32[D] (closest_docs as a map, 0xFFFFFFFF = none),
         ``catchwords`` a list of k word-id arrays.  Returns (Model float32[V, k], (doc, topic, sum) arrays in
         (doc, topic) order, top_topic_pairs int64[n, 3] in document order or None)."""
@@ -126,7 +127,8 @@ class SparseMatrix:
         cl = np.ascontiguousarray(cluster_of_doc, dtype=np.uint32)
         assert cl.shape[0] == self._num_docs
         # (doc_id_t)(eps3_c * w0_c * (FPTYPE)num_docs() / ((FPTYPE)num_topics * 2.0))   (:716)
-        rank = int(np.uint64(EPS3_C * W0_C * float(np.float32(self._num_docs)) / (float(np.float32(k)) * 2.0)))
+        # document-sharded contexts pass the corpus-wide document count (the rank is a global quantity)
+        rank = int(np.uint64(EPS3_C * W0_C * float(np.float32(total_docs or self._num_docs)) / (float(np.float32(k)) * 2.0)))
         model = np.zeros((k, self._vocab_size), dtype=np.float32)
         n = C.c_uint64()
         self.ctx.call("isle_cuda_construct_topic_model", k, ptr(tw), ptr(cl), rank, ptr(model), C.byref(n))

@@ -26,7 +26,8 @@ from isle_b200.sparse_matrix import FPSparseMatrix, SparseMatrix  # noqa: E402
 from oracle import isle_oracle as O  # noqa: E402  (checker only)
 
 
-def stages(ctx, V, D, k, vals, rows, offsets, avg, nz, centers0=None, U_override=None, seed=3, full_centers0=None):
+def stages(ctx, V, D, k, vals, rows, offsets, avg, nz, centers0=None, U_override=None, seed=3, full_centers0=None,
+           total_docs=None):
     A = SparseMatrix(V, D, ctx)
     A.populate_normalized(vals, rows, offsets, avg, nz)
     z, nn = A.compute_thresholds(0, V, None, k)
@@ -48,7 +49,15 @@ def stages(ctx, V, D, k, vals, rows, offsets, avg, nz, centers0=None, U_override
     full_in = full.copy()
     B.cleanup_after_eigensolver()
     B.run_lloyds(k, full, None, 10)
-    return dict(row_sharded=row_sharded, z=z, nn=nn, bv=bv, br=br, bo=bo, oc=oc, ev=ev, U=U, seeds=seeds, coords=coords, centers=c0,
+    # stages G / H from that partition: thresholds and catchwords are global quantities, the
+    # (doc, topic) sums are local, the model is allreduced
+    cl = np.full(D, 0xFFFFFFFF, np.uint32)
+    cl[oc.astype(np.int64)] = B.last_lloyd_full["assign"]
+    thr = A.catchword_thresholds(k, O.catchword_rank(total_docs or D, k), cl)
+    cw = A.find_catchwords(k, None)
+    model, dts, _ = A.construct_topic_model(k, cl, cw, want_pairs=False, total_docs=total_docs or D)
+    return dict(catch_thr=thr, catchwords=cw, model=model, dts=dts, row_sharded=row_sharded,
+                z=z, nn=nn, bv=bv, br=br, bo=bo, oc=oc, ev=ev, U=U, seeds=seeds, coords=coords, centers=c0,
                 obj=B.last_lloyd["objective"], assign=B.last_lloyd["assign"], iters=B.last_lloyd["iters"],
                 full_in=full_in, full=full, full_obj=B.last_lloyd_full["objective"], full_assign=B.last_lloyd_full["assign"],
                 full_iters=B.last_lloyd_full["iters"])
@@ -74,7 +83,7 @@ def main():
     # the check covers the row-sharded Krylov basis unless told otherwise (the library's default switches it on only for
     # bases that stream from HBM)
     sh.set_option("ks_row_shard", 0 if os.environ.get("ISLE_KS_ROW_SHARD") == "0" else 1)
-    r = stages(sh, c.V, d1 - d0, c.k, vals[e0:e1], c.rows[e0:e1], lo, float(avg), nz_local)
+    r = stages(sh, c.V, d1 - d0, c.k, vals[e0:e1], c.rows[e0:e1], lo, float(avg), nz_local, total_docs=c.D)
     # the single-GPU run; its k-means stages get the sharded run's U and k-means++ centers so that
     # both Lloyd runs see the same projection and start identically
     one = _capi.Context(local)
@@ -132,6 +141,18 @@ def main():
     check(abs(r["full_obj"] - s["full_obj"]) <= 1e-9 * s["full_obj"], "full-dimensional Lloyd objective differs")
     if len(sel):
         check(np.array_equal(s["full_assign"][sel], r["full_assign"]), "full-dimensional Lloyd assignments differ")
+    # stages G / H: thresholds (distributed radix select) and catchwords bit-identical, local (doc, topic) sums = the
+    # slice of the single-GPU list, the allreduced model within fp32 rounding
+    check(np.array_equal(r["catch_thr"].view(np.uint32), s["catch_thr"].view(np.uint32)), "catchword thresholds differ")
+    check(all(np.array_equal(a, b) for a, b in zip(r["catchwords"], s["catchwords"])), "catchwords differ")
+    sd, st_, sv = s["dts"]
+    m = (sd >= d0) & (sd < d1)
+    rd, rt, rv = r["dts"]
+    check(np.array_equal(sd[m] - d0, rd) and np.array_equal(st_[m], rt) and np.array_equal(sv[m].view(np.uint32), rv.view(np.uint32)),
+          "document-topic sums differ")
+    okm = ~np.isnan(s["model"])
+    check(np.array_equal(np.isnan(r["model"]), ~okm) and
+          np.max(np.abs(r["model"][okm] - s["model"][okm])) <= 1e-6 * np.max(np.abs(s["model"][okm])), "topic model differs")
     # k-means++ seeds are global column ids of B and must be distinct
     check(len(set(r["seeds"].tolist())) == c.k and int(r["seeds"].max()) < len(s["oc"]), "bad k-means++ seeds")
     flag = torch.tensor([0 if ok else 1], device="cuda")

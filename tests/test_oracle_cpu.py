@@ -325,3 +325,45 @@ def test_reference_side_binding_covers_every_member():
                "SparseMatrix<float>::construct_topic_model("]
     for m in members:
         assert any(("ISLE::" + m) in s for s in strong), f"{m} is not bound to the shim"
+
+
+def test_distributed_radix_select_model():
+    """numpy model of seg_select.cuh: the (kth + 1)-th largest float of every segment from four rounds of byte
+    histograms that are summed over 'ranks' (here: arbitrary splits of the values), compared with a sort."""
+    rng = np.random.default_rng(2)
+    nseg, n, world = 37, 20000, 3
+    seg = rng.integers(0, nseg, n).astype(np.int64)
+    val = np.concatenate([rng.random(n // 2).astype(np.float32) * 50, np.round(rng.random(n - n // 2) * 8).astype(np.float32)])  # ties
+    val[::97] = -val[::97]                                       # the ordered map must handle negative values too
+    owner = rng.integers(0, world, n)
+    bits = val.view(np.uint32).astype(np.uint64)
+    ordered = np.where(bits & 0x80000000, (~bits) & 0xFFFFFFFF, bits | 0x80000000).astype(np.uint64)
+    cnt = np.bincount(seg, minlength=nseg)
+    kth = np.minimum(rng.integers(0, 600, nseg), cnt - 1).astype(np.int64)
+    kth[cnt == 0] = -1                                           # 0xFFFFFFFF in the kernel: no selection
+    rem, prefix = kth.copy(), np.zeros(nseg, np.uint64)
+    for rnd in range(4):
+        hist = np.zeros((nseg, 256), np.int64)
+        for rk in range(world):                                  # per-rank histograms, then the allreduce
+            m = owner == rk
+            ok = m & ((rnd == 0) | ((ordered >> np.uint64(32 - 8 * rnd)) == prefix[seg])) if rnd else m
+            byte = ((ordered[ok] >> np.uint64(24 - 8 * rnd)) & np.uint64(255)).astype(np.int64)
+            np.add.at(hist, (seg[ok], byte), 1)
+        for s in range(nseg):                                    # pick_kernel
+            if kth[s] < 0:
+                continue
+            b = 255
+            while b > 0:
+                if rem[s] < hist[s, b]:
+                    break
+                rem[s] -= hist[s, b]
+                b -= 1
+            prefix[s] = (prefix[s] << np.uint64(8)) | np.uint64(b)
+    for s in range(nseg):
+        if kth[s] < 0:
+            continue
+        o = prefix[s]
+        b32 = np.uint32(o & np.uint64(0x7FFFFFFF)) if (o & np.uint64(0x80000000)) else np.uint32((~o) & np.uint64(0xFFFFFFFF))
+        got = np.array([b32], dtype=np.uint32).view(np.float32)[0]
+        want = np.sort(val[seg == s])[::-1][kth[s]]
+        assert got == want, (s, got, want)
