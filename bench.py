@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--cpu-sample-docs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--opt", nargs="*", default=[], help="library options name=value (isle_cuda_set_option), for A/B runs")
     ap.add_argument("--e2e-skip-B-U", dest="e2e_skip_B_U", action="store_true",
                     help="e2e leg without the B / U downloads the reference-side shim makes (round-1 behaviour)")
     return ap.parse_args()
@@ -342,7 +343,8 @@ STAT_NAMES = ("launches", "spmm_bt_ms", "spmm_bt_bytes", "spmm_bt_calls", "spmm_
               "dist_tc_ms", "dist_simt_ms", "dist_tc_flops", "dist_simt_flops", "lloyd_accum_ms", "ks_wtf_ms", "ks_wtf_bytes",
               "ks_wtfred_ms", "ks_fsub_ms", "ks_fsub_bytes", "pp_dist_tc_ms", "pp_dist_skinny_ms", "pp_dist_simt_ms",
               "split_p_ms", "spmm_head1_ms", "spmm_tail1_ms", "spmm_head2_ms", "spmm_tail2_ms", "spmm_head_words",
-              "spmm_tail_nnz", "alloc_misses", "alloc_hits", "allreduce_ms", "lift_ms", "ks_evd_ms")
+              "spmm_tail_nnz", "alloc_misses", "alloc_hits", "allreduce_ms", "allgather_ms", "lift_ms", "ks_evd_ms", "ks_row_sharded",
+              "allreduce_calls", "allgather_calls")
 
 
 def ours_line(*, args, world, cfg_name, D, V, nnz, k, sha16, total_docs, dev_ms, e2e_s, h2d, d2h, st, state, clocks,
@@ -365,7 +367,8 @@ def ours_line(*, args, world, cfg_name, D, V, nnz, k, sha16, total_docs, dev_ms,
         "run": {"D_B": state["DB"], "nnz_B": state["nnzB"], "ks_restarts": st["ks_restarts"],
                 "ks_block_steps": st["ks_ops"], "ks_gs_third_passes_elided": st["ks_gs_elided"],
                 "spmm_head_words": int(st["spmm_head_words"]), "spmm_tail_nnz": int(st["spmm_tail_nnz"]),
-                "lloyd_iters": state["iters"], "nconv": state["nconv"]},
+                "lloyd_iters": state["iters"], "nconv": state["nconv"], "ks_row_sharded": bool(st.get("ks_row_sharded", 0.0)),
+                "options": list(getattr(args, "opt", []) or [])},
         # the e2e leg moves what the reference-side shim moves: A up (u64 row ids), zetas, all of B (vals, u64 rows,
         # offsets, original_cols), eigenvalues, U, seeds, projected centers and the lifted centers down
         "e2e": {"value": (total_docs * args.steps / e2e_s) if e2e_s and e2e_s != float("inf") else None, "unit": UNIT,
@@ -418,6 +421,9 @@ def bench_ours(args):
         dist.broadcast(idt, 0)
         nccl_id = bytes(idt.cpu().numpy().tobytes())
     ctx = _capi.Context(local, rank, world, nccl_id)
+    for o in args.opt:
+        name, val = o.split("=")
+        ctx.set_option(name, int(val))
 
     cfg = corpus.CONFIGS[args.config]
     V, k = cfg["V"], cfg["k"]
