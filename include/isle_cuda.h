@@ -61,6 +61,27 @@ int isle_cuda_upload_A(isle_cuda_ctx *ctx, uint64_t V, uint64_t D, int64_t nnz,
 int isle_cuda_upload_A_u32(isle_cuda_ctx *ctx, uint64_t V, uint64_t D, int64_t nnz,
                            const float *normalized_vals, const uint32_t *rows,
                            const int64_t *offsets, float avg_doc_sz, uint64_t nz_docs);
+/* ingest on the device.  Replaces DocWordEntriesReader::fill_doc_word_entries (include/utils.h:160-228:
+ * `<doc> <word> <count>` lines, 1-based ids, blanks / tabs between the fields, optional '\r', a last line without '\n'),
+ * the sort + de-duplication of finalize_data (src/trainer.cpp:232-246; of duplicated (doc, word) lines the first in file
+ * order survives), SparseMatrix::populate_CSC (src/sparseMatrix.cpp:58-106; avg_doc_sz = (float)(tokens / non-empty docs),
+ * integer division) and SparseMatrix::normalize_docs (src/sparseMatrix.cpp:136-167), bit-exactly.  `text` is the file's
+ * bytes (mmap it as the reference does), max_entries its line count (<= 0: not checked; the reference asserts equality,
+ * utils.h:227).  The result is the uploaded A of the context (isle_cuda_thresholds may follow directly); *nnz_out = entries
+ * after de-duplication, *avg_doc_sz_out / *nz_docs_out / *tokens_out the statistics populate_CSC prints.  A malformed line
+ * or an id out of range -> ISLE_ERR_RANGE; so is a document of 2^24 tokens or more (its fp32 token sum, exact and order
+ * independent below that, is what makes the normalisation reproducible).  In a sharded context `text` holds the rank's
+ * documents (D = the local count, doc ids local) and the statistics are those of the whole corpus. */
+int isle_cuda_ingest_text(isle_cuda_ctx *ctx, const char *text, uint64_t size, uint64_t V, uint64_t D, int64_t max_entries,
+                          int64_t *nnz_out, float *avg_doc_sz_out, uint64_t *nz_docs_out, uint64_t *tokens_out);
+/* populate_CSC's statistics + normalize_docs (src/sparseMatrix.cpp:86-98, 136-167) for a doc-major CSC of RAW counts that
+ * is already sorted and de-duplicated: uploads it, normalises on the device (same exactness check), leaves A ready for
+ * isle_cuda_thresholds. */
+int isle_cuda_upload_counts(isle_cuda_ctx *ctx, uint64_t V, uint64_t D, int64_t nnz, const uint32_t *counts, const uint32_t *rows,
+                            const int64_t *offsets, float *avg_doc_sz_out, uint64_t *nz_docs_out);
+/* Copies the context's A out in the reference's host layout (normalized_vals_CSC f32[nnz], rows_CSC u64[nnz],
+ * offsets_CSC i64[D+1], include/sparseMatrix.h:23-38) for the members that stay on the host.  Any pointer may be NULL. */
+int isle_cuda_download_A(isle_cuda_ctx *ctx, float *normalized_vals, uint64_t *rows, int64_t *offsets);
 /* Replaces list_word_freqs_by_sorting + compute_thresholds
  * (src/sparseMatrix.cpp:289-333, 357-485).  zetas_out: V floats; *new_nnz_out = number of
  * entries with round(value) >= zeta (the function's return value).  In a sharded context both are

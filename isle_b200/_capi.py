@@ -53,6 +53,9 @@ SIGNATURES = {
     "isle_cuda_nccl_unique_id": [_vp],
     "isle_cuda_upload_A": [_vp, _u64, _u64, _i64, _vp, _vp, _vp, _f32, _u64],
     "isle_cuda_upload_A_u32": [_vp, _u64, _u64, _i64, _vp, _vp, _vp, _f32, _u64],
+    "isle_cuda_ingest_text": [_vp, _vp, _u64, _u64, _u64, _i64, C.POINTER(_i64), C.POINTER(_f32), C.POINTER(_u64), C.POINTER(_u64)],
+    "isle_cuda_upload_counts": [_vp, _u64, _u64, _i64, _vp, _vp, _vp, C.POINTER(_f32), C.POINTER(_u64)],
+    "isle_cuda_download_A": [_vp, _vp, _vp, _vp],
     "isle_cuda_thresholds": [_vp, _u64, _vp, C.POINTER(_i64)],
     "isle_cuda_build_B": [_vp, _vp, C.POINTER(_i64), C.POINTER(_u64)],
     "isle_cuda_sampling_weights": [_vp, _vp],

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libisle_cuda.so")
-SOURCES = ["capi.cu", "threshold.cu", "spmm.cu", "spmm_head.cu", "spmm_head_i8.cu", "blockks.cu", "panel_tc.cu", "kmeans.cu", "dist_tc.cu", "lloyd_full.cu", "catchwords.cu", "topic_model.cu", "coll.cu"]
+SOURCES = ["capi.cu", "threshold.cu", "spmm.cu", "spmm_head.cu", "spmm_head_i8.cu", "blockks.cu", "panel_tc.cu", "kmeans.cu", "dist_tc.cu", "lloyd_full.cu", "catchwords.cu", "topic_model.cu", "coll.cu", "ingest.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

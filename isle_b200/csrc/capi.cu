@@ -176,6 +176,23 @@ int isle_cuda_upload_A_u32(isle_cuda_ctx *h, uint64_t V, uint64_t D, int64_t nnz
     return guarded(h, [&](Ctx &c) { upload_A(c, V, D, nnz, vals, rows, false, offsets, avg, nz_docs); });
 }
 
+int isle_cuda_ingest_text(isle_cuda_ctx *h, const char *text, uint64_t size, uint64_t V, uint64_t D, int64_t max_entries,
+                          int64_t *nnz_out, float *avg_doc_sz_out, uint64_t *nz_docs_out, uint64_t *tokens_out)
+{
+    return guarded(h, [&](Ctx &c) { ingest_text(c, text, size, V, D, max_entries, nnz_out, avg_doc_sz_out, nz_docs_out, tokens_out); });
+}
+
+int isle_cuda_upload_counts(isle_cuda_ctx *h, uint64_t V, uint64_t D, int64_t nnz, const uint32_t *counts, const uint32_t *rows,
+                            const int64_t *offsets, float *avg_doc_sz_out, uint64_t *nz_docs_out)
+{
+    return guarded(h, [&](Ctx &c) { upload_counts(c, V, D, nnz, counts, rows, offsets, avg_doc_sz_out, nz_docs_out); });
+}
+
+int isle_cuda_download_A(isle_cuda_ctx *h, float *normalized_vals, uint64_t *rows, int64_t *offsets)
+{
+    return guarded(h, [&](Ctx &c) { download_A(c, normalized_vals, rows, offsets); });
+}
+
 int isle_cuda_thresholds(isle_cuda_ctx *h, uint64_t k, float *zetas_out, int64_t *new_nnz_out)
 {
     return guarded(h, [&](Ctx &c) { compute_thresholds(c, k, zetas_out, new_nnz_out); });

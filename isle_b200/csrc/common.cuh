@@ -342,6 +342,13 @@ void sample_docs(Ctx &c, float sample_rate, uint64_t seed, uint8_t *select_out, 
 void download_B(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets, uint64_t *orig);
 float frobenius(Ctx &c);
 
+// ---- ingest.cu (text -> entries -> CSC -> normalised A on the device)
+void ingest_text(Ctx &c, const char *text, uint64_t size, uint64_t V, uint64_t D, int64_t max_entries, int64_t *nnz_out,
+                 float *avg_out, uint64_t *nz_docs_out, uint64_t *tokens_out);
+void upload_counts(Ctx &c, uint64_t V, uint64_t D, int64_t nnz, const uint32_t *counts, const uint32_t *rows, const int64_t *offsets,
+                   float *avg_out, uint64_t *nz_docs_out);
+void download_A(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets);
+
 // ---- spmm.cu
 void build_csr(Ctx &c, bool head_i8 = true);
 // Z(V x b, column-major, ld=V) = B (B^T X); X column-major ld=V; both on the device.

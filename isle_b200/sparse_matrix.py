@@ -74,6 +74,36 @@ class SparseMatrix:
         self.ctx.call(fn, self._vocab_size, self._num_docs, self._nnzs, ptr(vals), ptr(rows), ptr(offs),
                       C.c_float(self.avg_doc_sz), self._nz_docs)
 
+    def ingest_text(self, text: bytes, max_entries: int = 0) -> None:
+        """ISLETrainer's ingest on the device: DocWordEntriesReader (include/utils.h:160-228), the sort
+        and de-duplication of finalize_data (src/trainer.cpp:232-246), populate_CSC and normalize_docs
+        (src/sparseMatrix.cpp:58-167).  ``text`` holds `<doc> <word> <count>` lines; afterwards the object is in the
+        state populate_normalized leaves it in."""
+        buf = np.frombuffer(text, dtype=np.uint8)
+        nnz, avg, nz, tok = C.c_int64(), C.c_float(), C.c_uint64(), C.c_uint64()
+        self.ctx.call("isle_cuda_ingest_text", ptr(buf) if len(buf) else None, len(buf), self._vocab_size, self._num_docs,
+                      int(max_entries), C.byref(nnz), C.byref(avg), C.byref(nz), C.byref(tok))
+        self._nnzs, self.avg_doc_sz, self._nz_docs, self.total_tokens = int(nnz.value), float(avg.value), int(nz.value), int(tok.value)
+
+    def populate_CSC_and_normalize(self, counts, rows, offsets) -> None:
+        """populate_CSC's statistics + normalize_docs (src/sparseMatrix.cpp:86-98, 136-167) on the device for a sorted,
+        de-duplicated doc-major CSC of raw counts."""
+        cnt = np.ascontiguousarray(counts, dtype=np.uint32)
+        rws = np.ascontiguousarray(rows, dtype=np.uint32)
+        offs = np.ascontiguousarray(offsets, dtype=np.int64)
+        avg, nz = C.c_float(), C.c_uint64()
+        self.ctx.call("isle_cuda_upload_counts", self._vocab_size, self._num_docs, int(offs[-1]), ptr(cnt), ptr(rws), ptr(offs),
+                      C.byref(avg), C.byref(nz))
+        self._nnzs, self.avg_doc_sz, self._nz_docs = int(offs[-1]), float(avg.value), int(nz.value)
+
+    def download(self):
+        """The normalised CSC in the reference's host layout: (normalized_vals f32, rows u64, offsets i64)."""
+        vals = np.zeros(self._nnzs, dtype=np.float32)
+        rows = np.zeros(self._nnzs, dtype=np.uint64)
+        offs = np.zeros(self._num_docs + 1, dtype=np.int64)
+        self.ctx.call("isle_cuda_download_A", ptr(vals), ptr(rows), ptr(offs))
+        return vals, rows, offs
+
     def list_word_freqs_by_sorting(self):
         """src/sparseMatrix.cpp:289-333.  ``freqs`` is only a hand-off to compute_thresholds;
         the device path needs no word-major lists, so this is a no-op returning a token."""

@@ -28,6 +28,57 @@ import scipy.sparse as sp
 F32 = np.float32
 
 
+# --------------------------------------------------------------------------- ingest
+def parse_entries(text: bytes):
+    """include/utils.h:160-228 DocWordEntriesReader::fill_doc_word_entries, restated character by character (small
+    inputs only): digits accumulate into the 1st / 2nd / 3rd field of the line, a digit after blanks or tabs starts the
+    next field, '\r' is ignored, '\n' emits the entry with 0-based doc and word, a last line without '\n' is emitted
+    if its third field was reached.  Returns (doc, word, count) int64 arrays in file order."""
+    docs, words, counts = [], [], []
+    doc = word = count = 0
+    state, was_ws = 1, False
+    for ch in text:
+        c = chr(ch)
+        if c == "\r":
+            continue
+        if c == "\n":
+            docs.append(doc - 1); words.append(word - 1); counts.append(count)
+            doc = word = count = 0
+            state = 1
+            was_ws = False      # (the reference leaves was_whitespace set across lines; lines never start with blanks here)
+        elif c in " \t":
+            was_ws = True
+        elif c.isdigit():
+            if was_ws:
+                state += 1
+                was_ws = False
+            assert state <= 3, "Bad line"
+            if state == 1:
+                doc = doc * 10 + int(c)
+            elif state == 2:
+                word = word * 10 + int(c)
+            else:
+                count = count * 10 + int(c)
+        else:
+            raise ValueError("Bad format")
+    if state == 3:
+        docs.append(doc - 1); words.append(word - 1); counts.append(count)
+    return np.array(docs, np.int64), np.array(words, np.int64), np.array(counts, np.int64)
+
+
+def entries_to_csc(docs, words, counts, D: int):
+    """src/trainer.cpp:237-246 (sort by (doc, word), std::unique keeps the first of each (doc, word) -- here the first in
+    file order) + src/sparseMatrix.cpp:58-84 populate_CSC: (offsets i64[D+1], rows u32, counts u32)."""
+    order = np.lexsort((words, docs))            # stable: file order among equals
+    d, w, c = docs[order], words[order], counts[order]
+    first = np.ones(len(d), dtype=bool)
+    first[1:] = (d[1:] != d[:-1]) | (w[1:] != w[:-1])
+    d, w, c = d[first], w[first], c[first]
+    offsets = np.zeros(D + 1, dtype=np.int64)
+    np.cumsum(np.bincount(d, minlength=D), out=offsets[1:])
+    return offsets, w.astype(np.uint32), c.astype(np.uint32)
+
+
 # --------------------------------------------------------------------------- stage 0
 def normalize_docs(counts, offsets):
     """src/sparseMatrix.cpp:86-98 (avg_doc_sz, nz_docs) and :136-167 (normalize_docs).

@@ -574,6 +574,69 @@ def test_topic_model_corner_cases(ctx):
     assert np.max(np.abs(M[:, :5] - M_o[:, :5])) <= 1e-6 * np.max(np.abs(M_o[:, :5]))
 
 
+# ---------------------------------------------------------------- ingest
+def _corpus_text(c, shuffle_seed=None):
+    docs = np.repeat(np.arange(c.D, dtype=np.int64), np.diff(c.offsets))
+    arr = np.stack([docs + 1, c.rows.astype(np.int64) + 1, c.counts.astype(np.int64)], 1)
+    if shuffle_seed is not None:
+        arr = arr[np.random.default_rng(shuffle_seed).permutation(len(arr))]
+    import io
+    buf = io.BytesIO()
+    np.savetxt(buf, arr, fmt="%d")
+    return buf.getvalue()
+
+
+@pytest.mark.parametrize("name", ["tiny", "c1"])
+def test_ingest_text_matches_reference(ctx, name, golden_tiny, golden_c1, corpus_c1):
+    """Text -> CSC -> normalised A on the device against the reference's own ingest output (ref_dump stage 0), from the
+    shuffled text form of the corpus: offsets, rows, normalised values bit-exact; then thresholds straight from it."""
+    from isle_b200 import corpus
+    from isle_b200.sparse_matrix import SparseMatrix
+    g = golden_tiny if name == "tiny" else golden_c1
+    c = corpus.generate("tiny") if name == "tiny" else corpus_c1
+    A = SparseMatrix(c.V, c.D, ctx)
+    A.ingest_text(_corpus_text(c, shuffle_seed=5), max_entries=c.nnz)
+    vals, rows, offs = A.download()
+    assert A.get_nnzs() == c.nnz and A.avg_doc_sz == float(g["avg_doc_sz"]) and A._nz_docs == c.D
+    assert np.array_equal(offs, c.offsets) and np.array_equal(rows, c.rows.astype(np.uint64))
+    assert sha(vals) == str(g["A_vals_sha"])
+    zetas, nn = A.compute_thresholds(0, c.V, None, c.k)
+    assert np.array_equal(zetas, g["zetas"]) and nn == int(g["new_nnzs"])
+
+
+def test_ingest_text_edge_cases_and_errors(ctx):
+    from isle_b200._capi import IsleCudaError
+    from isle_b200.sparse_matrix import SparseMatrix
+    text = b"2 3 4\r\n1\t\t5   6\n2 3 9\n4 1 1\n5 5 7\n5 2 1"     # CRLF, tabs, duplicate (doc, word), empty doc 3, no final newline
+    d, w, n = O.parse_entries(text)
+    offsets, rows, counts = O.entries_to_csc(d, w, n, 6)
+    vals_o, avg_o, nz_o = O.normalize_docs(counts, offsets)
+    A = SparseMatrix(5, 6, ctx)
+    A.ingest_text(text, max_entries=6)
+    vals, r, offs = A.download()
+    assert np.array_equal(offs, offsets) and np.array_equal(r, rows.astype(np.uint64))
+    assert np.array_equal(vals.view(np.uint32), vals_o.view(np.uint32)) and A.avg_doc_sz == float(avg_o) and A._nz_docs == nz_o
+    for bad in (b"1 2 x\n", b"1 2\n", b"7 1 1\n", b"1 6 1\n", b"0 1 1\n", b"1 1 1 1\n"):
+        with pytest.raises(IsleCudaError):
+            SparseMatrix(5, 6, ctx).ingest_text(bad)
+    with pytest.raises(IsleCudaError):                              # the reference asserts nRead == max_entries
+        SparseMatrix(5, 6, ctx).ingest_text(text, max_entries=7)
+    with pytest.raises(IsleCudaError):                              # 2^24 tokens in one document: fp32 doc_sum no longer exact
+        SparseMatrix(5, 6, ctx).ingest_text(b"1 1 16777216\n1 2 5\n")
+
+
+def test_populate_csc_and_normalize_on_device(ctx, golden_c1, corpus_c1):
+    """a2 of SURVEY 8: populate_CSC's statistics + normalize_docs on the device from the sorted CSC of raw counts."""
+    from isle_b200.sparse_matrix import SparseMatrix
+    g, c = golden_c1, corpus_c1
+    A = SparseMatrix(c.V, c.D, ctx)
+    A.populate_CSC_and_normalize(c.counts, c.rows, c.offsets)
+    vals, rows, offs = A.download()
+    vals_o, avg_o, nz_o = O.normalize_docs(c.counts, c.offsets)
+    assert np.array_equal(vals.view(np.uint32), vals_o.view(np.uint32)) and sha(vals) == str(g["A_vals_sha"])
+    assert A.avg_doc_sz == float(avg_o) and A._nz_docs == nz_o
+
+
 # ---------------------------------------------------------------- end to end
 def test_spectral_core_end_to_end_c1(ctx, golden_c1, corpus_c1):
     """Stages A-E through the public call; k-means is checked through rotation-invariant

@@ -367,3 +367,33 @@ def test_distributed_radix_select_model():
         got = np.array([b32], dtype=np.uint32).view(np.float32)[0]
         want = np.sort(val[seg == s])[::-1][kth[s]]
         assert got == want, (s, got, want)
+
+
+# ---------------------------------------------------------------- ingest
+def _corpus_text(c, shuffle_seed=None):
+    docs = np.repeat(np.arange(c.D, dtype=np.int64), np.diff(c.offsets))
+    lines = [f"{d + 1} {w + 1} {n}" for d, w, n in zip(docs, c.rows.astype(np.int64), c.counts.astype(np.int64))]
+    if shuffle_seed is not None:
+        np.random.default_rng(shuffle_seed).shuffle(lines)
+    return ("\n".join(lines) + "\n").encode()
+
+
+def test_oracle_ingest_reproduces_the_reference_csc(golden_tiny):
+    """The reference's own ingest output (ref_dump stage 0: CSC built by populate_CSC from the sorted entries, values from
+    normalize_docs) from the text form of the same corpus, lines shuffled."""
+    from isle_b200 import corpus
+    g = golden_tiny
+    c = corpus.generate("tiny")
+    d, w, n = O.parse_entries(_corpus_text(c, shuffle_seed=3))
+    offsets, rows, counts = O.entries_to_csc(d, w, n, c.D)
+    assert np.array_equal(offsets, g["offsets"]) and np.array_equal(rows, g["rows"]) and np.array_equal(counts, g["counts"])
+    vals, avg, nz = O.normalize_docs(counts, offsets)
+    assert np.array_equal(vals.view(np.uint32), g["A_normalized_vals"].view(np.uint32)) and float(avg) == float(g["avg_doc_sz"])
+
+
+def test_oracle_parser_edge_cases():
+    text = b"2 3 4\r\n1\t\t5   6\n2 3 9\n4 1 1"          # CRLF, tabs / several blanks, a duplicate (doc, word), no final newline
+    d, w, n = O.parse_entries(text)
+    assert d.tolist() == [1, 0, 1, 3] and w.tolist() == [2, 4, 2, 0] and n.tolist() == [4, 6, 9, 1]
+    offsets, rows, counts = O.entries_to_csc(d, w, n, 5)
+    assert offsets.tolist() == [0, 1, 2, 2, 3, 3] and rows.tolist() == [4, 2, 0] and counts.tolist() == [6, 4, 1]   # first duplicate kept
