@@ -46,6 +46,15 @@ int isle_cuda_create(isle_cuda_ctx **ctx, int device);
 int isle_cuda_create_sharded(isle_cuda_ctx **ctx, int device, int rank, int world,
                              const void *nccl_id);
 int isle_cuda_nccl_unique_id(void *id128);
+/* Multi-GPU context in ONE process (isle_cuda_create(ctx**, n_gpus)): what a single-threaded caller such as
+ * ISLETrainer::train() binds to use every GPU of the box.  n_gpus devices (`devices` lists them, NULL = 0 .. n_gpus-1),
+ * one host thread and one document-sharded per-GPU context per device inside the library, communicators from
+ * ncclCommInitAll.  Every entry point below accepts such a context with the SAME arguments as a single-GPU one: host
+ * arrays describe the whole corpus; the library cuts the documents into n contiguous ranges, runs on all GPUs at once
+ * and returns per-document outputs (B, original_cols, assignments, (doc, topic) sums) stitched together in document
+ * order, global outputs (zetas, eigenpairs, centers, thresholds, the model) from GPU 0.  Not available on it:
+ * isle_cuda_sample_docs, isle_cuda_ingest_text, isle_cuda_upload_counts, isle_cuda_download_A. */
+int isle_cuda_create_multi(isle_cuda_ctx **ctx, int n_gpus, const int *devices);
 void isle_cuda_destroy(isle_cuda_ctx *ctx);
 const char *isle_cuda_last_error(const isle_cuda_ctx *ctx);
 

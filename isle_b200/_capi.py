@@ -51,6 +51,7 @@ SIGNATURES = {
     "isle_cuda_create": [_pp, _int],
     "isle_cuda_create_sharded": [_pp, _int, _int, _int, _vp],
     "isle_cuda_nccl_unique_id": [_vp],
+    "isle_cuda_create_multi": [_pp, _int, _vp],
     "isle_cuda_upload_A": [_vp, _u64, _u64, _i64, _vp, _vp, _vp, _f32, _u64],
     "isle_cuda_upload_A_u32": [_vp, _u64, _u64, _i64, _vp, _vp, _vp, _f32, _u64],
     "isle_cuda_ingest_text": [_vp, _vp, _u64, _u64, _u64, _i64, C.POINTER(_i64), C.POINTER(_f32), C.POINTER(_u64), C.POINTER(_u64)],
@@ -107,9 +108,11 @@ def ptr(a):
 class Context:
     """Owns one isle_cuda_ctx (one GPU, one caller thread)."""
 
-    def __init__(self, device: int = 0, rank: int = 0, world: int = 1, nccl_id: bytes | None = None):
+    def __init__(self, device: int = 0, rank: int = 0, world: int = 1, nccl_id: bytes | None = None, n_gpus: int = 0):
         h = C.c_void_p()
-        if world > 1:
+        if n_gpus > 1:       # one process, n_gpus devices, one host thread per device inside the library
+            rc = lib.isle_cuda_create_multi(C.byref(h), n_gpus, None)
+        elif world > 1:
             buf = C.create_string_buffer(nccl_id, 128)
             rc = lib.isle_cuda_create_sharded(C.byref(h), device, rank, world, buf)
         else:

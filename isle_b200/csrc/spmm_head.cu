@@ -383,7 +383,7 @@ void launch_head_t(Ctx &c, const __nv_bfloat16 *split, uint64_t kpad, const Head
     const uint32_t smem_bytes = p.stages * stage_bytes + 1024 + 512;
     ISLE_CUDA_CHECK(cudaFuncSetAttribute(spmm_head_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     if (c.head_diag_dev) {
-        static uint32_t *installed = nullptr;     // device-side symbol, set once per process and pointer
+        static thread_local uint32_t *installed = nullptr;     // device-side symbol, set once per host thread (= per device) and pointer
         if (installed != c.head_diag_dev) {
             ISLE_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_head_diag, &c.head_diag_dev, sizeof(uint32_t *), 0, cudaMemcpyHostToDevice, stream));
             installed = c.head_diag_dev;

@@ -434,7 +434,7 @@ void spmm_head_i8_launch(Ctx &c, int b, const uint4 *bits, uint32_t num_mtiles, 
     const uint32_t smem_bytes = p.slab * kScBytes + p.stages * (p.slab ? kBitBytes : kScBytes + kBitBytes) + 1024 + 512;
     ISLE_CUDA_CHECK(cudaFuncSetAttribute(spmm_head_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     if (c.head_diag_dev) {
-        static uint32_t *installed = nullptr;     // device-side symbol, set once per process and pointer
+        static thread_local uint32_t *installed = nullptr;     // device-side symbol, set once per host thread (= per device) and pointer
         if (installed != c.head_diag_dev) {
             ISLE_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_head8_diag, &c.head_diag_dev, sizeof(uint32_t *), 0, cudaMemcpyHostToDevice, stream));
             installed = c.head_diag_dev;

@@ -52,8 +52,25 @@ isle_cuda_ctx *g_ctx = nullptr;
 isle_cuda_ctx *ctx()
 {
     if (!g_ctx) {
+        // ISLE_CUDA_NGPUS=n (or ISLE_CUDA_DEVICES=0,1,...): every GPU of the box behind the one context train() uses --
+        // the library shards the documents itself (isle_cuda_create_multi); default: one GPU, ISLE_CUDA_DEVICE
         const char *dev = std::getenv("ISLE_CUDA_DEVICE");
-        const int rc = isle_cuda_create(&g_ctx, dev ? std::atoi(dev) : 0);
+        const char *ngpus = std::getenv("ISLE_CUDA_NGPUS");
+        const char *list = std::getenv("ISLE_CUDA_DEVICES");
+        int rc;
+        if (list && *list) {
+            std::vector<int> devs;
+            for (const char *p = list; *p;) {
+                devs.push_back(std::atoi(p));
+                while (*p && *p != ',') ++p;
+                if (*p == ',') ++p;
+            }
+            rc = isle_cuda_create_multi(&g_ctx, (int)devs.size(), devs.data());
+        } else if (ngpus && std::atoi(ngpus) > 1) {
+            rc = isle_cuda_create_multi(&g_ctx, std::atoi(ngpus), nullptr);
+        } else {
+            rc = isle_cuda_create(&g_ctx, dev ? std::atoi(dev) : 0);
+        }
         if (rc != ISLE_OK)
             throw std::runtime_error(std::string("libisle_cuda: ") + isle_cuda_last_error(nullptr));
     }
