@@ -118,6 +118,13 @@ int isle_cuda_sample_docs(isle_cuda_ctx *ctx, float sample_rate, uint64_t seed, 
  * Any pointer may be NULL to skip that array. */
 int isle_cuda_download_B(isle_cuda_ctx *ctx, float *vals, uint64_t *rows, int64_t *offsets,
                          uint64_t *original_cols);
+/* The same copy in the background: _begin stages the arrays on the device and returns; a host thread inside the library
+ * moves them to the caller's arrays over a separate copy stream while later calls (isle_cuda_block_ks ...) run; _end waits
+ * for it.  The arrays must stay valid and unread until _end returns.  threshold_and_copy's host arrays are read by nothing
+ * on the spectral core (train() goes on with the device's B), so the replacement translation unit starts the download in
+ * threshold_and_copy and ends it after compute_block_ks.  Calls that rebuild A or B end a pending download first. */
+int isle_cuda_download_B_begin(isle_cuda_ctx *ctx, float *vals, uint64_t *rows, int64_t *offsets, uint64_t *original_cols);
+int isle_cuda_download_B_end(isle_cuda_ctx *ctx);
 /* FPSparseMatrix::frobenius (src/sparseMatrix.cpp:1096-1100): sum of squares of B. */
 int isle_cuda_frobenius(isle_cuda_ctx *ctx, float *out);
 

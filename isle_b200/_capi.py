@@ -61,6 +61,8 @@ SIGNATURES = {
     "isle_cuda_build_B": [_vp, _vp, C.POINTER(_i64), C.POINTER(_u64)],
     "isle_cuda_sampling_weights": [_vp, _vp],
     "isle_cuda_download_B": [_vp, _vp, _vp, _vp, _vp],
+    "isle_cuda_download_B_begin": [_vp, _vp, _vp, _vp, _vp],
+    "isle_cuda_download_B_end": [_vp],
     "isle_cuda_frobenius": [_vp, C.POINTER(_f32)],
     "isle_cuda_spsptr_multiply": [_vp, _int, _vp, _vp],
     "isle_cuda_block_ks": [_vp, _u64, _int, _int, _f32, _u64, _vp, _vp, C.POINTER(_int)],

@@ -368,7 +368,9 @@ void isle_cuda_destroy(isle_cuda_ctx *h)
     cudaSetDevice(c.device);
     tls_stream() = c.stream;
     tls_cache() = &c.cache;
+    if (c.dl_active) { try { download_B_end(c); } catch (...) {} }
     if (c.stream) cudaStreamSynchronize(c.stream);
+    if (c.copy_stream) { cudaStreamDestroy(c.copy_stream); cudaEventDestroy(c.ev_copy); }
     for (auto &kv : c.stats)
         for (auto &ev : kv.second.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
 #ifdef ISLE_WITH_NCCL
@@ -451,6 +453,18 @@ int isle_cuda_download_B(isle_cuda_ctx *h, float *vals, uint64_t *rows, int64_t 
 {
     if (h && h->g) return m_download_B(*h->g, vals, rows, offsets, orig);
     return guarded(h, [&](Ctx &c) { download_B(c, vals, rows, offsets, orig); });
+}
+
+int isle_cuda_download_B_begin(isle_cuda_ctx *h, float *vals, uint64_t *rows, int64_t *offsets, uint64_t *orig)
+{
+    if (h && h->g) return m_download_B(*h->g, vals, rows, offsets, orig);      // multi-GPU: stitched synchronously
+    return guarded(h, [&](Ctx &c) { download_B_begin(c, vals, rows, offsets, orig); });
+}
+
+int isle_cuda_download_B_end(isle_cuda_ctx *h)
+{
+    if (h && h->g) return ISLE_OK;
+    return guarded(h, [&](Ctx &c) { download_B_end(c); });
 }
 
 int isle_cuda_frobenius(isle_cuda_ctx *h, float *out)

@@ -11,6 +11,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/isle_cuda.h"
@@ -257,6 +258,16 @@ struct Ctx {
     DevBuf<float> lifted;                  // last lift_centers result (V x lifted_cols, column-major): input of lloyd_full
     uint64_t lifted_cols = 0;
 
+    // ---- background download of B (download_B_begin / _end): a copy stream and a host thread move B to the caller's arrays
+    // while the main stream goes on with the eigensolver
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr;
+    std::thread dl_thread;
+    bool dl_active = false;
+    std::string dl_error;
+    DevBuf<float> dl_vals;
+    DevBuf<unsigned long long> dl_rows, dl_orig;
+
     // ---- stats / options
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     bool profiling = false;
@@ -340,6 +351,8 @@ void build_B(Ctx &c, const uint8_t *select, int64_t *nnzB, uint64_t *DB);
 void sampling_weights(Ctx &c, float *out);
 void sample_docs(Ctx &c, float sample_rate, uint64_t seed, uint8_t *select_out, uint64_t *n_selected_out);
 void download_B(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets, uint64_t *orig);
+void download_B_begin(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets, uint64_t *orig);
+void download_B_end(Ctx &c);
 float frobenius(Ctx &c);
 
 // ---- ingest.cu (text -> entries -> CSC -> normalised A on the device)

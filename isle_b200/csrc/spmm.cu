@@ -853,6 +853,23 @@ static void launch_gather_bfp(Ctx &c, int b, bool add, const WorkItem *items, si
     count_launch(c);
 }
 
+// Experiment hook (option spmm_dummy_head): a kernel that only OCCUPIES what the head engine occupies on every SM -- one CTA,
+// 1024 thread slots (the tail keeps 4 of its 8 CTAs, as beside the real head), `smem` bytes of shared memory -- and sleeps
+// for `ns`.  Tells how fast the tail gather runs beside an idle co-tenant, i.e. whether sharing the SM or sharing the
+// L2 -> SM fabric is what slows it down beside the real head.
+__global__ void __launch_bounds__(1024)
+occupy_kernel(unsigned long long ns)
+{
+    extern __shared__ uint8_t dummy_smem[];
+    if (threadIdx.x == 0) dummy_smem[0] = 1;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < ns);
+}
+
 void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z)
 {
     ISLE_REQUIRE(c.have_B, ISLE_ERR_ARG, "spsptr_multiply: build_B first");
@@ -880,6 +897,12 @@ void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z)
     ISLE_CUDA_CHECK(cudaMemsetAsync(c.zbuf.p, 0, c.zbuf.bytes(), c.stream));
     // head engine of pass 1 (rows = documents, K = head ranks) / pass 2 (rows = head ranks, K = documents)
     auto head1 = [&](bool zero_out, bool force_atomic, cudaStream_t st) {
+        if (const int dummy_us = c.opt("spmm_dummy_head", 0)) {
+            const int smem = c.opt("spmm_dummy_smem_kb", 57) * 1024;
+            cudaFuncSetAttribute(occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            occupy_kernel<<<c.num_sms, 1024, smem, st>>>((unsigned long long)dummy_us * 1000ull);
+            return;
+        }
         if (i8) spmm_head_i8_launch(c, b, c.bits1.p, c.DBpad / kHeadTile, H / 256, 1, c.xdig.p, nullptr, c.ybuf.p, DB, zero_out, force_atomic, st);
         else spmm_head_launch(c, b, c.bits1.p, c.DBpad / kHeadTile, H / kHeadChunk, 1, c.xsplit.p, c.ybuf.p, DB, zero_out, force_atomic, st);
     };

@@ -44,6 +44,7 @@ __global__ void check_rows_kernel(const uint32_t *__restrict__ rows, int64_t n, 
 void upload_A(Ctx &c, uint64_t V, uint64_t D, int64_t nnz, const float *vals, const void *rows,
               bool rows64, const int64_t *offsets, float avg, uint64_t nz_docs)
 {
+    download_B_end(c);
     ISLE_REQUIRE(V > 0 && V < (1ull << 32) && D < (1ull << 32) && nnz >= 0, ISLE_ERR_ARG,
                  "upload_A: V, D must fit 32 bits");
     ISLE_REQUIRE(avg >= 1.0f && avg < 1.0e6f, ISLE_ERR_RANGE, "upload_A: avg_doc_sz out of range");
@@ -164,6 +165,7 @@ zeta_kernel(const uint32_t *__restrict__ hist, uint32_t V, int bins, uint32_t co
 
 void compute_thresholds(Ctx &c, uint64_t k, float *zetas_out, int64_t *new_nnz_out)
 {
+    download_B_end(c);
     ISLE_REQUIRE(c.a_off.p != nullptr, ISLE_ERR_ARG, "thresholds: upload_A first");
     ISLE_REQUIRE(k >= 1, ISLE_ERR_ARG, "thresholds: k must be >= 1");
     // src/sparseMatrix.cpp:370-373, evaluated on the host in double exactly as written there
@@ -289,6 +291,7 @@ compact_kernel(const float *__restrict__ val, const uint32_t *__restrict__ row,
 
 void build_B(Ctx &c, const uint8_t *select, int64_t *nnzB_out, uint64_t *DB_out)
 {
+    download_B_end(c);
     ISLE_REQUIRE(c.have_zeta, ISLE_ERR_ARG, "build_B: compute thresholds first");
     const uint32_t D = (uint32_t)c.D;
     DevBuf<uint8_t> dsel;
@@ -490,6 +493,63 @@ void download_B(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets, uint64_t 
         ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
     }
     ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+// The same copy in the background.  threshold_and_copy (src/sparseMatrix.cpp:1285-1361) leaves B in host arrays that
+// nothing on the spectral core reads again (the device keeps its own B), so the 12 bytes per nonzero need not hold the
+// eigensolver up: the expanded arrays are staged on the device, a host thread moves them over a separate copy stream
+// (DMA from the copy engine; staged through the driver's bounce buffers when the caller's arrays are pageable, which is why
+// it is a thread and not just an async call), and download_B_end() joins it.  The caller's arrays must stay valid and
+// unread until then.  One download at a time; anything that rebuilds B ends a pending one first.
+void download_B_begin(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets, uint64_t *orig)
+{
+    ISLE_REQUIRE(c.have_B, ISLE_ERR_ARG, "download_B_begin: build_B first");
+    download_B_end(c);
+    const int64_t n = c.nnzB;
+    if (!c.copy_stream) {
+        ISLE_CUDA_CHECK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        ISLE_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
+    }
+    c.dl_vals.alloc((vals && n) ? (size_t)n : 0);
+    c.dl_rows.alloc((rows && n) ? (size_t)n : 0);
+    c.dl_orig.alloc((orig && c.DB) ? (size_t)c.DB : 0);
+    if ((vals || rows) && n) {
+        expand_B_kernel<<<grid_for((size_t)n, 256), 256, 0, c.stream>>>(c.b_row.p, c.sqrt_zeta.p, n, c.dl_vals.p, c.dl_rows.p);
+        count_launch(c);
+    }
+    if (orig && c.DB) {
+        widen_u32_kernel<<<grid_for((size_t)c.DB, 256), 256, 0, c.stream>>>(c.b_orig.p, c.dl_orig.p, (int64_t)c.DB, 0ull);
+        count_launch(c);
+    }
+    ISLE_CUDA_CHECK(cudaEventRecord(c.ev_copy, c.stream));
+    c.dl_error.clear();
+    c.dl_active = true;
+    Ctx *cp = &c;
+    const size_t DB = (size_t)c.DB;
+    c.dl_thread = std::thread([cp, vals, rows, offsets, orig, n, DB] {
+        Ctx &c = *cp;
+        auto chk = [&](cudaError_t e, const char *what) {
+            if (e != cudaSuccess && c.dl_error.empty()) c.dl_error = std::string(what) + ": " + cudaGetErrorString(e);
+        };
+        chk(cudaSetDevice(c.device), "cudaSetDevice");
+        chk(cudaStreamWaitEvent(c.copy_stream, c.ev_copy, 0), "cudaStreamWaitEvent");
+        if (vals && n) chk(cudaMemcpyAsync(vals, c.dl_vals.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c.copy_stream), "copy vals");
+        if (rows && n) chk(cudaMemcpyAsync(rows, c.dl_rows.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c.copy_stream), "copy rows");
+        if (offsets) chk(cudaMemcpyAsync(offsets, c.b_off.p, (DB + 1) * 8, cudaMemcpyDeviceToHost, c.copy_stream), "copy offsets");
+        if (orig && DB) chk(cudaMemcpyAsync(orig, c.dl_orig.p, DB * 8, cudaMemcpyDeviceToHost, c.copy_stream), "copy original_cols");
+        chk(cudaStreamSynchronize(c.copy_stream), "cudaStreamSynchronize(copy)");
+    });
+}
+
+void download_B_end(Ctx &c)
+{
+    if (!c.dl_active) return;
+    if (c.dl_thread.joinable()) c.dl_thread.join();
+    c.dl_active = false;
+    c.dl_vals.release();
+    c.dl_rows.release();
+    c.dl_orig.release();
+    ISLE_REQUIRE(c.dl_error.empty(), ISLE_ERR_CUDA, "download_B (background): " + c.dl_error);
 }
 
 // frobenius = sum over nonzeros of sqrt_zeta[row]^2 = sum zeta[row]; the reference sums the

@@ -203,10 +203,12 @@ namespace ISLE
 
     // ---- stage B ----------------------------------------------------------------------------
     namespace {
+        // background = true: vals / rows / offsets arrive while train() goes on (isle_cuda_download_B_begin); nothing on the
+        // spectral core reads them, compute_block_ks() waits for the copy before it returns
         void build_and_download(FPSparseMatrix<float>& B, const uint8_t *mask, const offset_t nnzs,
                                 std::vector<doc_id_t>& original_cols,
                                 float *&vals, word_id_t *&rows, offset_t *&offsets,
-                                offset_t &nnzs_out, doc_id_t &docs_out)
+                                offset_t &nnzs_out, doc_id_t &docs_out, bool background = false)
         {
             int64_t nnzB = 0;
             uint64_t DB = 0;
@@ -216,8 +218,14 @@ namespace ISLE
             original_cols.resize(DB);
             static_assert(sizeof(doc_id_t) == sizeof(uint64_t) && sizeof(offset_t) == sizeof(int64_t),
                           "the C ABI assumes the reference's ILP64 index types");
-            check(isle_cuda_download_B(ctx(), vals, (uint64_t *)rows, (int64_t *)offsets,
-                                       (uint64_t *)original_cols.data()), "download_B");
+            if (background) {
+                // original_cols is read by train() right away (src/trainer.cpp:573-575): synchronously; the bulk in the background
+                check(isle_cuda_download_B(ctx(), NULL, NULL, NULL, (uint64_t *)original_cols.data()), "download_B");
+                check(isle_cuda_download_B_begin(ctx(), vals, (uint64_t *)rows, (int64_t *)offsets, NULL), "download_B_begin");
+            } else {
+                check(isle_cuda_download_B(ctx(), vals, (uint64_t *)rows, (int64_t *)offsets,
+                                           (uint64_t *)original_cols.data()), "download_B");
+            }
             nnzs_out = (offset_t)nnzB;
             docs_out = (doc_id_t)DB;
             (void)B;
@@ -236,7 +244,7 @@ namespace ISLE
         assert(original_cols.size() == 0); assert(zetas.size() == vocab_size());
         allocate(nnzs + 1000);                                  // src/sparseMatrix.cpp:1295-1296
         offset_t n = 0; doc_id_t d = 0;
-        build_and_download(*this, nullptr, nnzs, original_cols, vals_CSC, rows_CSC, offsets_CSC, n, d);
+        build_and_download(*this, nullptr, nnzs, original_cols, vals_CSC, rows_CSC, offsets_CSC, n, d, /*background=*/true);
         _num_docs = d;                                          // :1309
         std::cout << "Columns remaining after thresholding: " << d << "\n";
         _nnzs = n;                                              // :1320
@@ -305,6 +313,7 @@ namespace ISLE
                                           (float)BLOCK_KS_TOLERANCE, /*seed=*/0, ev.data(), U_colmajor, &nconv);
         // the reference asserts num_converged() == num_topics (:1207)
         check(rc, "block_ks");
+        check(isle_cuda_download_B_end(ctx()), "download_B_end");   // B's host arrays (threshold_and_copy) are complete from here on
         for (doc_id_t i = 0; i < num_topics; ++i) evalues.push_back(ev[i]);
         // U_rowmajor only feeds the host projection path this library replaces; stages F-H never
         // read it, so it is left unallocated (the destructor handles NULL).

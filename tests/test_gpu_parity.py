@@ -53,6 +53,27 @@ def test_thresholds_and_B_bit_exact_tiny(ctx, golden_tiny):
     assert abs(B.frobenius() - float(g["frobenius"])) <= 1e-6 * float(g["frobenius"])
 
 
+def test_background_download_of_B(ctx, golden_c1, corpus_c1):
+    """isle_cuda_download_B_begin / _end (what the shim's threshold_and_copy uses): the same arrays as the synchronous copy,
+    with the eigensolver running in between."""
+    from isle_b200._capi import ptr
+    g, c = golden_c1, corpus_c1
+    vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
+    A, B, zetas, nn, oc = make_AB(ctx, c.V, c.D, c.k, vals, c.rows, c.offsets, avg, nz)
+    bv, br, bo, boc = B.download()
+    v2, r2, o2, c2 = np.zeros_like(bv), np.zeros_like(br), np.zeros_like(bo), np.zeros_like(boc)
+    ctx.call("isle_cuda_download_B_begin", ptr(v2), ptr(r2), ptr(o2), ptr(c2))
+    ev = B.compute_block_ks(c.k, seed=1)
+    ctx.call("isle_cuda_download_B_end")
+    assert np.array_equal(v2, bv) and np.array_equal(r2, br) and np.array_equal(o2, bo) and np.array_equal(c2, boc)
+    assert sha(v2, r2.astype(np.uint32), o2, c2.astype(np.uint32)) == str(g["B_sha"])
+    ctx.call("isle_cuda_download_B_end")                             # idempotent
+    v3 = np.zeros_like(bv)
+    ctx.call("isle_cuda_download_B_begin", ptr(v3), None, None, None)
+    A2, B2, *_ = make_AB(ctx, c.V, c.D, c.k, vals, c.rows, c.offsets, avg, nz)     # rebuilding B ends the pending download first
+    assert np.array_equal(v3, bv)
+
+
 def test_u64_upload_path(ctx, golden_tiny):
     g = dict(golden_tiny)
     g["rows"] = g["rows"].astype(np.uint64)           # the reference's own index width
