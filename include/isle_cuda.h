@@ -233,6 +233,11 @@ int isle_cuda_doc_topic_sums(isle_cuda_ctx *ctx, uint32_t *docs, uint32_t *topic
  * column-major (ld n), updated in place; C_out: rows x b column-major (ld rows). */
 int isle_cuda_panel_products(isle_cuda_ctx *ctx, int64_t n, int rows, int b, const float *W,
                              float *F_inout, float *C_out, int engine);
+/* Harness only: the library's own collectives over peer memory (NVLink loads / stores + flags, coll.cu) run on many message
+ * sizes and types and are compared bit for bit with NCCL's.  *mismatches_out = differing elements over all ranks of a
+ * multi-GPU context / on this rank of a sharded one (0 expected); *p2p_active_out = 1 when the peer workspaces are mapped
+ * (0: single GPU, or NCCL carries every collective and nothing was compared).  Collective: every rank calls it. */
+int isle_cuda_selftest_collectives(isle_cuda_ctx *ctx, uint64_t *mismatches_out, int *p2p_active_out);
 /* cleanup_after_eigensolver (src/sparseMatrix.cpp:1264-1275): frees U, P and solver state. */
 int isle_cuda_cleanup_eigensolver(isle_cuda_ctx *ctx);
 

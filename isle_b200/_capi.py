@@ -81,6 +81,7 @@ SIGNATURES = {
     "isle_cuda_doc_topic_sums": [_vp, _vp, _vp, _vp],
     "isle_cuda_panel_products": [_vp, C.c_int64, _int, _int, _vp, _vp, _vp, _int],
     "isle_cuda_lloyd_full": [_vp, _u64, _vp, _int, _vp, C.POINTER(C.c_double), C.POINTER(_int)],
+    "isle_cuda_selftest_collectives": [_vp, C.POINTER(C.c_uint64), C.POINTER(_int)],
     "isle_cuda_cleanup_eigensolver": [_vp],
     "isle_cuda_set_profiling": [_vp, _int],
     "isle_cuda_get_stat": [_vp, C.c_char_p, C.POINTER(C.c_double)],

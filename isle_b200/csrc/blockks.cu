@@ -848,11 +848,22 @@ struct KsState {
     bool gs_elide = true;
     PanelTc ptc;
     DevBuf<int> drank, dinfo;
+    bool defer_rank = true;
+    int force_fallback = 0, fast_qr_calls = 0;
+    DevBuf<float> F2;          // second operator-output buffer (deferred rank check)
+    int *h_rank = nullptr;     // pinned
+    cudaEvent_t ev_rank = nullptr;
     int lwork = 0;
     int qr_grid = 1;
     int H_rows = 0, H_cols = 0;
     uint64_t seed, rng_calls = 0;
 
+    ~KsState()
+    {
+        if (h_rank) cudaFreeHost(h_rank);
+        if (ev_rank) cudaEventDestroy(ev_rank);
+    }
+    KsState(const KsState &) = delete;
     KsState(Ctx &ctx, int k_, int b_, uint64_t seed_) : c(ctx), n((int64_t)ctx.V), ng((int64_t)ctx.V), k(k_), b(b_), ps(ctx), seed(seed_)
     {
         ncv = 2 * k + b;
@@ -896,6 +907,15 @@ struct KsState {
         }
         drank.alloc(1);
         dinfo.alloc(1);
+        // deferred QR rank check (ks_defer_rank, default on): the rank of block step j is read from pinned memory only after
+        // the operator of step j + 1 has been queued, so the host round trip hides behind ~0.4 ms of GPU work instead
+        // of idling the device 41 (c2) / 1200 (c3) times per run; the next operator output goes to the other F buffer so that a
+        // rank-deficient block (rare) can still be re-factorised by the fallback QR and the operator redone
+        defer_rank = c.opt("ks_defer_rank", 1) != 0;
+        force_fallback = c.opt("ks_force_qr_fallback", 0);
+        F2.alloc((size_t)n * b);
+        ISLE_CUDA_CHECK(cudaHostAlloc((void **)&h_rank, sizeof(int), cudaHostAllocDefault));
+        ISLE_CUDA_CHECK(cudaEventCreateWithFlags(&ev_rank, cudaEventDisableTiming));
         ISLE_CUDA_CHECK(cudaMemsetAsync(V.p, 0, V.bytes(), c.stream));
         ISLE_CUDA_CHECK(cudaMemsetAsync(H.p, 0, H.bytes(), c.stream));
         ISLE_CUSOLVER_CHECK(cusolverDnSsyevd_bufferSize(c.cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER,
@@ -971,53 +991,66 @@ struct KsState {
         return rank;
     }
 
-    // [Q,R] = mgs_qr64(Fsrc); Q -> Qdst (ld n); R -> Rb (b x b, zero padded).  Returns rank.
-    int qr(const float *Fsrc, int cols, float *Qdst)
+    // CholeskyQR2 fast path, launch only: Q -> Qdst, R -> Rb, the rank (or -1: bad pivot, the fallback must run) travels to
+    // pinned memory behind an event.  Rb must have been zeroed by the caller.
+    void qr_fast_launch(const float *Fsrc, int cols, float *Qdst)
     {
-        ISLE_CUDA_CHECK(cudaMemsetAsync(Rb.p, 0, Rb.bytes(), c.stream));
-        StatScope s(c, "ks_qr");
-        int rank = -1;
+        CholQrParams q;
+        q.F = Fsrc; q.n = n; q.b = cols; q.Q = Qdst; q.R = Rb.p; q.rank_out = drank.p; q.part = cpart.p;
         if (shard) {
-            if (fast_qr) {
-                CholQrParams q;
-                q.F = Fsrc; q.n = n; q.b = cols; q.Q = Qdst; q.R = Rb.p; q.rank_out = drank.p; q.part = cpart.p;
-                gram_rows_kernel<<<chol_grid, 256, kCholDynSmem, c.stream>>>(q, nullptr);
-                sum_partials_kernel<<<1, 256, 0, c.stream>>>(cpart.p, (unsigned)chol_grid, gram1.p);
-                allreduce_sum_f64(c, gram1.p, 256);
-                gram_rows_kernel<<<chol_grid, 256, kCholDynSmem, c.stream>>>(q, gram1.p);
-                sum_partials_kernel<<<1, 256, 0, c.stream>>>(cpart.p, (unsigned)chol_grid, gram2.p);
-                allreduce_sum_f64(c, gram2.p, 256);
-                cholqr2_finish_kernel<<<chol_grid, 256, 0, c.stream>>>(q, gram1.p, gram2.p);
-                count_launch(c, 5);
-                ISLE_CUDA_CHECK(cudaMemcpyAsync(&rank, drank.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-                ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-                if (rank >= 0) return rank;
-                c.counters["ks_qr_fallbacks"] += 1.0;
-            }
-            return qr_gathered(Fsrc, cols, Qdst);
-        }
-        if (fast_qr) {
-            CholQrParams q;
-            q.F = Fsrc; q.n = n; q.b = cols; q.Q = Qdst; q.R = Rb.p; q.rank_out = drank.p; q.part = cpart.p;
+            gram_rows_kernel<<<chol_grid, 256, kCholDynSmem, c.stream>>>(q, nullptr);
+            sum_partials_kernel<<<1, 256, 0, c.stream>>>(cpart.p, (unsigned)chol_grid, gram1.p);
+            allreduce_sum_f64(c, gram1.p, 256);
+            gram_rows_kernel<<<chol_grid, 256, kCholDynSmem, c.stream>>>(q, gram1.p);
+            sum_partials_kernel<<<1, 256, 0, c.stream>>>(cpart.p, (unsigned)chol_grid, gram2.p);
+            allreduce_sum_f64(c, gram2.p, 256);
+            cholqr2_finish_kernel<<<chol_grid, 256, 0, c.stream>>>(q, gram1.p, gram2.p);
+            count_launch(c, 5);
+        } else {
             void *qargs[] = {&q};
             ISLE_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)cholqr2_kernel, dim3(chol_grid), dim3(256), qargs,
                                                         kCholDynSmem, c.stream));
             count_launch(c);
-            ISLE_CUDA_CHECK(cudaMemcpyAsync(&rank, drank.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-            ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-            if (rank >= 0) return rank;
-            c.counters["ks_qr_fallbacks"] += 1.0;
-            ISLE_CUDA_CHECK(cudaMemsetAsync(Rb.p, 0, Rb.bytes(), c.stream));
         }
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(h_rank, drank.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        ISLE_CUDA_CHECK(cudaEventRecord(ev_rank, c.stream));
+    }
+    int qr_fast_result()
+    {
+        ISLE_CUDA_CHECK(cudaEventSynchronize(ev_rank));
+        // test hook (ks_force_qr_fallback = N): every N-th fast QR is treated as a bad pivot, so the fallback / redo path runs
+        if (force_fallback > 0 && ++fast_qr_calls % force_fallback == 0) return -1;
+        return *h_rank;
+    }
+    // the reference's modified Gram-Schmidt (rank revealing), on the gathered block when the basis is row-sharded
+    int qr_slow(const float *Fsrc, int cols, float *Qdst)
+    {
+        if (shard) return qr_gathered(Fsrc, cols, Qdst);
+        ISLE_CUDA_CHECK(cudaMemsetAsync(Rb.p, 0, Rb.bytes(), c.stream));
         QrParams p;
         p.F = Fsrc; p.n = n; p.b = cols; p.a = qa.p; p.q = qq.p; p.Q = Qdst; p.R = Rb.p;
         p.rank_out = drank.p; p.part = qpart.p;
         void *args[] = {&p};
         ISLE_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)mgs_qr64_kernel, dim3(qr_grid), dim3(256), args, 0, c.stream));
         count_launch(c);
+        int rank = -1;
         ISLE_CUDA_CHECK(cudaMemcpyAsync(&rank, drank.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
         ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
         return rank;
+    }
+
+    // [Q,R] = mgs_qr64(Fsrc); Q -> Qdst (ld n); R -> Rb (b x b, zero padded).  Returns rank.
+    int qr(const float *Fsrc, int cols, float *Qdst)
+    {
+        ISLE_CUDA_CHECK(cudaMemsetAsync(Rb.p, 0, Rb.bytes(), c.stream));
+        StatScope s(c, "ks_qr");
+        if (fast_qr) {
+            qr_fast_launch(Fsrc, cols, Qdst);
+            const int rank = qr_fast_result();
+            if (rank >= 0) return rank;
+            c.counters["ks_qr_fallbacks"] += 1.0;
+        }
+        return qr_slow(Fsrc, cols, Qdst);
     }
     // NOTE: for cols < b the R rows use leading dimension `cols`; callers that need R pass cols == b.
 
@@ -1116,11 +1149,41 @@ struct KsState {
     }
 
     // restarted_block_ks.h:63-136
+    // A deferred rank check comes due: the fast QR of the block step that wrote Vcol(rows) from Fsrc.  true = full rank,
+    // nothing to do; false = the block was re-factorised by the rank-revealing QR and / or refilled (Vcol(rows) and the R
+    // block of H changed: whatever was computed from them since must be redone).
+    bool resolve_rank(int rows, int cols, const float *Fsrc)
+    {
+        int rk = qr_fast_result();
+        if (rk == b) return true;
+        if (rk < 0) {
+            c.counters["ks_qr_fallbacks"] += 1.0;
+            StatScope s(c, "ks_qr");
+            rk = qr_slow(Fsrc, b, Vcol(rows));
+            ISLE_CUDA_CHECK(cudaMemcpy2DAsync(Hat(rows, cols), (size_t)ncv * 4, Rb.p, (size_t)b * 4, (size_t)b * 4, b,
+                                              cudaMemcpyDeviceToDevice, c.stream));
+        }
+        if (rk < b) {
+            ISLE_CUDA_CHECK(cudaMemsetAsync(Vcol(rows + rk), 0, (size_t)(b - rk) * n * 4, c.stream));
+            refill(rows + rk, rows + b);
+        }
+        return false;
+    }
+
     void expand()
     {
+        const bool defer = defer_rank && fast_qr;
+        bool pending = false;
+        int p_rows = 0, p_cols = 0, step = 0;
+        const float *p_F = nullptr;
         while (H_rows < ncv) {
             const int rows = H_rows, cols = H_cols;
-            op(Vcol(cols), F.p);                                          // F = A V_k
+            float *Fc = (defer && (step++ & 1)) ? F2.p : F.p;
+            op(Vcol(cols), Fc);                                           // F = A V_k
+            if (pending) {      // the rank of the block this operator was just applied to, read behind the queued work
+                pending = false;
+                if (!resolve_rank(p_rows, p_cols, p_F)) op(Vcol(cols), Fc);
+            }
             {
                 StatScope s(c, "ks_orth", 2.0 * gs_passes * (double)n * rows * 4.0, 4.0 * gs_passes * (double)n * rows * b);
                 float *Hk = Hat(0, cols);
@@ -1129,24 +1192,24 @@ struct KsState {
                     // moved coefficients below 1e-4 of the first's, what is left along W is below fp32 resolution
                     // of H and the third pass is elided on the device (no host round trip; ks_gs_elide = 0 keeps it).
                     ptc.begin_step(c);
-                    ptc.split_F(c, F.p, b);
+                    ptc.split_F(c, Fc, b);
                     for (int pass = 0; pass < gs_passes; ++pass) {
                         ptc.wtf(c, V.p, rows, b, C.p, ncv, Hk, ncv, pass == 0, gs_elide ? pass : 0);
-                        ptc.fsub(c, V.p, rows, b, F.p, gs_elide ? pass : 0);
+                        ptc.fsub(c, V.p, rows, b, Fc, gs_elide ? pass : 0);
                         if (gs_elide && pass == 1 && gs_passes > 2) ptc.decide_elision(c, 1e-4f);
                     }
                 } else if (custom_orth) {
                     // Hk = W^T F ; F -= W Hk ; then (gs_passes - 1) x { Ck = W^T F ; F -= W Ck ; Hk += Ck }
                     for (int pass = 0; pass < gs_passes; ++pass) {
-                        ps.wtf(V.p, rows, b, F.p, C.p, ncv, Hk, pass == 0);
-                        ps.fsub(V.p, rows, b, C.p, ncv, F.p);
+                        ps.wtf(V.p, rows, b, Fc, C.p, ncv, Hk, pass == 0);
+                        ps.fsub(V.p, rows, b, C.p, ncv, Fc);
                     }
                 } else {
-                    gemm_tn(rows, b, V.p, F.p, Hk, ncv);                      // Hk = W^T F
-                    gemm_sub(rows, b, V.p, Hk, ncv, F.p);                     // F -= W Hk
+                    gemm_tn(rows, b, V.p, Fc, Hk, ncv);                      // Hk = W^T F
+                    gemm_sub(rows, b, V.p, Hk, ncv, Fc);                     // F -= W Hk
                     for (int pass = 0; pass + 1 < gs_passes; ++pass) {
-                        gemm_tn(rows, b, V.p, F.p, C.p, ncv);                 // Ck = W^T F
-                        gemm_sub(rows, b, V.p, C.p, ncv, F.p);                // F -= W Ck
+                        gemm_tn(rows, b, V.p, Fc, C.p, ncv);                 // Ck = W^T F
+                        gemm_sub(rows, b, V.p, C.p, ncv, Fc);                // F -= W Ck
                         add_block_kernel<<<(rows * b + 255) / 256, 256, 0, c.stream>>>(Hk, ncv, C.p, ncv, rows, b);
                         count_launch(c);
                     }
@@ -1155,7 +1218,21 @@ struct KsState {
                 zero_block_kernel<<<(b * (cols + b) + 255) / 256, 256, 0, c.stream>>>(Hat(rows, 0), ncv, b, cols + b);
                 count_launch(c);
             }
-            const int rk = qr(F.p, b, Vcol(rows));
+            if (defer) {
+                ISLE_CUDA_CHECK(cudaMemsetAsync(Rb.p, 0, Rb.bytes(), c.stream));
+                {
+                    StatScope s(c, "ks_qr");
+                    qr_fast_launch(Fc, b, Vcol(rows));
+                }
+                ISLE_CUDA_CHECK(cudaMemcpy2DAsync(Hat(rows, cols), (size_t)ncv * 4, Rb.p, (size_t)b * 4, (size_t)b * 4, b,
+                                                  cudaMemcpyDeviceToDevice, c.stream));
+                pending = true;
+                p_rows = rows; p_cols = cols; p_F = Fc;
+                H_rows += b;
+                H_cols += b;
+                continue;
+            }
+            const int rk = qr(Fc, b, Vcol(rows));
             ISLE_CUDA_CHECK(cudaMemcpy2DAsync(Hat(rows, cols), (size_t)ncv * 4, Rb.p, (size_t)b * 4, (size_t)b * 4, b,
                                               cudaMemcpyDeviceToDevice, c.stream));
             H_rows += b;
@@ -1165,6 +1242,7 @@ struct KsState {
                 refill(rows + rk, rows + b);
             }
         }
+        if (pending) resolve_rank(p_rows, p_cols, p_F);
     }
 
     // restarted_block_ks.h:139-187

@@ -373,6 +373,7 @@ void isle_cuda_destroy(isle_cuda_ctx *h)
     if (c.copy_stream) { cudaStreamDestroy(c.copy_stream); cudaEventDestroy(c.ev_copy); }
     for (auto &kv : c.stats)
         for (auto &ev : kv.second.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    p2p_destroy(c);
 #ifdef ISLE_WITH_NCCL
     if (c.comm) ncclCommDestroy(c.comm);
 #endif
@@ -465,6 +466,22 @@ int isle_cuda_download_B_end(isle_cuda_ctx *h)
 {
     if (h && h->g) return ISLE_OK;
     return guarded(h, [&](Ctx &c) { download_B_end(c); });
+}
+
+int isle_cuda_selftest_collectives(isle_cuda_ctx *h, uint64_t *mismatches_out, int *p2p_active_out)
+{
+    if (!mismatches_out || !p2p_active_out) return ISLE_ERR_ARG;
+    *mismatches_out = 0;
+    *p2p_active_out = 0;
+    std::mutex mu;
+    return guarded_all(h, [&](Ctx &c) {
+        unsigned long long m = 0;
+        int a = 0;
+        selftest_collectives(c, &m, &a);
+        std::lock_guard<std::mutex> lk(mu);
+        *mismatches_out += m;
+        *p2p_active_out |= a;
+    });
 }
 
 int isle_cuda_frobenius(isle_cuda_ctx *h, float *out)

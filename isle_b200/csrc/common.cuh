@@ -268,6 +268,15 @@ struct Ctx {
     DevBuf<float> dl_vals;
     DevBuf<unsigned long long> dl_rows, dl_orig;
 
+    // ---- peer-to-peer collectives over NVLink / NVSwitch (coll.cu): one workspace per rank that every other rank maps
+    // into its own address space (cudaIpc between processes, peer access inside one process)
+    int p2p_state = 0;                     // 0 not tried yet, 1 ready, -1 unavailable (NCCL carries every collective)
+    char *p2p_ws[16] = {};                 // [world] the workspace of every rank as THIS device addresses it
+    bool p2p_ipc[16] = {};                 // mapped with cudaIpcOpenMemHandle (closed on destroy)
+    unsigned long long p2p_epoch = 0;      // one per collective; identical on every rank (same call sequence)
+    unsigned p2p_cnt_a = 0, p2p_cnt_b = 0; // cumulative CTA-arrival targets of the two grid-level counters
+    uint32_t *p2p_diag_host = nullptr, *p2p_diag_dev = nullptr;   // host-mapped record of a timed-out wait
+
     // ---- stats / options
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     bool profiling = false;
@@ -447,5 +456,7 @@ void allgather_u64(Ctx &c, const unsigned long long *send, unsigned long long *r
 void allgather_f64(Ctx &c, const double *send, double *recv);                         // 1 per rank
 void bcast_f32(Ctx &c, float *buf, size_t n, int root);
 void allgather_f32(Ctx &c, const float *send, float *recv, size_t count);   // `count` floats per rank
+void p2p_destroy(Ctx &c);
+void selftest_collectives(Ctx &c, unsigned long long *mismatches_out, int *p2p_active_out);   // P2P vs NCCL, bit for bit                                                    // unmaps / frees the peer workspace
 
 }  // namespace isle

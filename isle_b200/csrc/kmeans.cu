@@ -630,6 +630,32 @@ __global__ void pick_kernel(const double *__restrict__ cumul, uint32_t n, const 
     out[i] = offset + (lo < n ? lo : n - 1) + 1ull;
 }
 
+// The same with the draw itself on the device: thread i turns the uniform u[i] into the threshold total * u[i] (total = sum
+// of the ranks' partial totals, added in rank order as the host would), finds the rank whose share of the prefix sums holds
+// it (never an empty shard) and, on that rank, the document.  Saves the host round trip that fetched the totals.
+struct PpDraws { double u[64]; };
+__global__ void pick_draws_kernel(const double *__restrict__ cumul, uint32_t n, const double *__restrict__ tot_all, int world, int rank,
+                                  PpDraws dr, int nt, unsigned long long offset, unsigned long long *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    double prefix[17];
+    prefix[0] = 0.0;
+    for (int r = 0; r < world; ++r) prefix[r + 1] = prefix[r] + tot_all[r];
+    const double t = prefix[world] * dr.u[i];
+    int r = 0;
+    while (r + 1 < world && t >= prefix[r + 1]) ++r;
+    while (r > 0 && tot_all[r] <= 0.0) --r;
+    if (r != rank || n == 0) { out[i] = 0ull; return; }
+    const double tv = fmax(0.0, t - prefix[r]);
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (cumul[mid] > tv) hi = mid; else lo = mid + 1;
+    }
+    out[i] = offset + (lo < n ? lo : n - 1) + 1ull;
+}
+
 __global__ void fill_kernel(float *__restrict__ p, size_t n, float v)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -702,32 +728,22 @@ void kmeanspp(Ctx &c, uint64_t k64, uint64_t seed, uint64_t *seeds_out, float *c
             ISLE_CUDA_CHECK(cudaMemsetAsync(tot_mine.p, 0, 8, c.stream));
         }
         allgather_f64(c, tot_mine.p, tot_all.p);
-        ISLE_CUDA_CHECK(cudaMemcpyAsync(totals.data(), tot_all.p, totals.size() * 8, cudaMemcpyDeviceToHost, c.stream));
-        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-        prefix[0] = 0.0;
-        for (int r = 0; r < c.world; ++r) prefix[r + 1] = prefix[r] + totals[r];
-        total = prefix[c.world];
-        // draw 1 + sqrt(max(s-5,0)) candidates (:2181-2199); duplicates are skipped
+        // draw 1 + sqrt(max(s-5,0)) candidates (:2181-2199); duplicates are skipped.  The uniforms come from the host
+        // generator (every rank draws the same), the thresholds total * u and their owners are worked out on the device, so
+        // the only host read of the round is the picked ids (with the totals riding along)
         const int s_now = (int)centers.size();
-        std::vector<double> ts;
-        for (int d = 0; d < 1 + std::sqrt((double)(s_now - 5 > 0 ? s_now - 5 : 0)) && (int)ts.size() < kMaxDraw; ++d)
-            ts.push_back(total * uni(rng));
-        const int ndraw = (int)ts.size();
-        // thresholds that fall into this rank's share of the prefix sums, made local
-        std::vector<double> tl(ndraw, -1.0);
-        for (int d = 0; d < ndraw; ++d) {
-            int r = 0;
-            while (r + 1 < c.world && ts[d] >= prefix[r + 1]) ++r;
-            while (r > 0 && totals[r] <= 0.0) --r;           // never hand a draw to an empty shard
-            if (r == c.rank && DB) tl[d] = std::max(0.0, ts[d] - prefix[r]);
-        }
-        ISLE_CUDA_CHECK(cudaMemcpyAsync(dt.p, tl.data(), (size_t)ndraw * 8, cudaMemcpyHostToDevice, c.stream));
-        pick_kernel<<<1, kMaxDraw, 0, c.stream>>>(cumul.p, DB, dt.p, ndraw, c.db_offset, gids.p);
+        PpDraws dr;
+        int ndraw = 0;
+        for (int d = 0; d < 1 + std::sqrt((double)(s_now - 5 > 0 ? s_now - 5 : 0)) && ndraw < kMaxDraw; ++d) dr.u[ndraw++] = uni(rng);
+        pick_draws_kernel<<<1, kMaxDraw, 0, c.stream>>>(cumul.p, DB, tot_all.p, c.world, c.rank, dr, ndraw, c.db_offset, gids.p);
         count_launch(c);
         if (c.world > 1) allreduce_sum_u64(c, gids.p, (size_t)ndraw);
         std::vector<unsigned long long> hg(ndraw);
         ISLE_CUDA_CHECK(cudaMemcpyAsync(hg.data(), gids.p, (size_t)ndraw * 8, cudaMemcpyDeviceToHost, c.stream));
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(totals.data(), tot_all.p, totals.size() * 8, cudaMemcpyDeviceToHost, c.stream));
         ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        total = 0.0;
+        for (int r = 0; r < c.world; ++r) total += totals[r];
         std::vector<uint64_t> fresh;
         for (int d = 0; d < ndraw && centers.size() + fresh.size() < k; ++d) {
             if (hg[d] == 0) continue;                       // no owner (total == 0)

@@ -83,6 +83,18 @@ def main():
     # the check covers the row-sharded Krylov basis unless told otherwise (the library's default switches it on only for
     # bases that stream from HBM)
     sh.set_option("ks_row_shard", 0 if os.environ.get("ISLE_KS_ROW_SHARD") == "0" else 1)
+    if os.environ.get("ISLE_P2P") == "0":
+        sh.set_option("p2p", 0)
+    # the library's own collectives over peer memory (coll.cu) against NCCL, bit for bit, before anything depends on them
+    import ctypes as C
+    st_mism, active = C.c_uint64(), C.c_int()
+    sh.call("isle_cuda_selftest_collectives", C.byref(st_mism), C.byref(active))
+    p2p_note = f"p2p collectives {'ON' if active.value else 'off (NCCL)'}, self-test mismatches {st_mism.value}"
+    p2p_bad = st_mism.value != 0 or (active.value == 0 and os.environ.get("ISLE_P2P") != "0")
+    if active.value and rank == 0:
+        print("collective latency us (p2p / nccl): " + ", ".join(
+            f"{sz} {sh.stat('selftest_p2p_' + sz + '_us'):.1f} / {sh.stat('selftest_nccl_' + sz + '_us'):.1f}" for sz in ("4mb", "50kb", "2kb")),
+            flush=True)
     r = stages(sh, c.V, d1 - d0, c.k, vals[e0:e1], c.rows[e0:e1], lo, float(avg), nz_local, total_docs=c.D)
     # the single-GPU run; its k-means stages get the sharded run's U and k-means++ centers so that
     # both Lloyd runs see the same projection and start identically
@@ -98,6 +110,7 @@ def main():
             ok = False
             print(f"[rank {rank}] FAIL: {msg}", flush=True)
 
+    check(not p2p_bad, p2p_note)
     check(np.array_equal(r["z"], s["z"]), "thresholds differ from the single-GPU run")
     # compute_thresholds returns the kept-entry count of the WHOLE corpus on every rank (include/isle_cuda.h)
     check(r["nn"] == s["nn"], f"kept-entry count {r['nn']} differs from the single-GPU run's {s['nn']}")
@@ -159,7 +172,8 @@ def main():
     dist.all_reduce(flag)
     if rank == 0:
         print(f"multi_gpu_check[{name}, world={world}]: sigma rel {rel:.2e}, angle {ang:.2e}, objective rel {obj_rel:.2e}, "
-              f"assign mismatch {mism:.2%}, lloyd iters {r['iters']}/{s['iters']} -> "
+              f"assign mismatch {mism:.2%}, lloyd iters {r['iters']}/{s['iters']}, {p2p_note}, "
+              f"p2p collectives used {sh.stat('p2p_collectives') if active.value else 0:.0f} -> "
               + ("OK" if int(flag.item()) == 0 else "FAILED"), flush=True)
     sh.close()
     one.close()

@@ -320,19 +320,24 @@ def test_panel_product_engines(ctx, engine, shape):
 
 @pytest.mark.parametrize("opts", [dict(ks_panel_tc=0, ks_panel_v2=0), dict(ks_panel_tc=0, ks_panel_v2=1), dict(ks_panel_tc=1),
                                   dict(ks_panel_tc=1, ks_gs_elide=0),
-                                  dict(ks_panel_tc=0, ks_panel_v2=0, ks_custom_orth=0, ks_fast_qr=0)],
-                         ids=["scalar-panels", "vector-panels", "tcgen05-panels", "tcgen05-panels-3-passes", "cublas-mgs"])
+                                  dict(ks_panel_tc=0, ks_panel_v2=0, ks_custom_orth=0, ks_fast_qr=0),
+                                  dict(ks_panel_tc=1, ks_defer_rank=0), dict(ks_panel_tc=1, ks_force_qr_fallback=3)],
+                         ids=["scalar-panels", "vector-panels", "tcgen05-panels", "tcgen05-panels-3-passes", "cublas-mgs",
+                              "rank-read-every-step", "forced-qr-fallback-and-redo"])
 def test_block_ks_engine_variants_c1(ctx, golden_c1, corpus_c1, opts):
     """Every panel / QR engine of the device solver meets the same bar against the reference's output."""
     g, c = golden_c1, corpus_c1
     vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
     A, B, *_ = make_AB(ctx, c.V, c.D, c.k, vals, c.rows, c.offsets, avg, nz)
-    defaults = dict(ks_panel_tc=1, ks_panel_v2=1, ks_custom_orth=1, ks_fast_qr=1, ks_gs_elide=1)
+    defaults = dict(ks_panel_tc=1, ks_panel_v2=1, ks_custom_orth=1, ks_fast_qr=1, ks_gs_elide=1, ks_defer_rank=1,
+                    ks_force_qr_fallback=0)
     try:
         for k_, v_ in {**defaults, **opts}.items():
             ctx.set_option(k_, v_)
         ev, U = B.compute_block_ks(c.k, seed=3, want_U=True)
         elided = ctx.stat("ks_gs_elided")
+        if opts.get("ks_force_qr_fallback"):      # the deferred check found the (simulated) bad pivots and re-did those steps
+            assert ctx.stat("ks_qr_fallbacks") >= 3
         # the third Gram-Schmidt pass is elided on the device only by the tensor-core engine, and only when allowed
         assert (elided > 0) == (opts.get("ks_panel_tc") == 1 and opts.get("ks_gs_elide", 1) == 1)
     finally:

@@ -121,6 +121,11 @@ def test_multi_gpu_context_matches_single_gpu_through_the_c_abi():
                     full_assign=B.last_lloyd_full["assign"], thr=thr, cw=cw, model=model, dts=dts, seeds=seeds)
 
     two = _capi.Context(n_gpus=2)
+    # the library's own collectives over peer memory (in one process: plain peer access) against NCCL, bit for bit
+    import ctypes as C
+    mism, active = C.c_uint64(), C.c_int()
+    two.call("isle_cuda_selftest_collectives", C.byref(mism), C.byref(active))
+    assert active.value == 1 and mism.value == 0
     r = run(two)
     assert two.stat("n_gpus") == 2 and two.stat("D_B") == len(r["oc"])
     two.close()
