@@ -344,7 +344,7 @@ STAT_NAMES = ("launches", "spmm_bt_ms", "spmm_bt_bytes", "spmm_bt_calls", "spmm_
               "ks_wtfred_ms", "ks_fsub_ms", "ks_fsub_bytes", "pp_dist_tc_ms", "pp_dist_skinny_ms", "pp_dist_simt_ms",
               "split_p_ms", "spmm_head1_ms", "spmm_tail1_ms", "spmm_head2_ms", "spmm_tail2_ms", "spmm_head_words",
               "spmm_tail_nnz", "alloc_misses", "alloc_hits", "allreduce_ms", "allgather_ms", "lift_ms", "ks_evd_ms", "ks_row_sharded",
-              "allreduce_calls", "allgather_calls")
+              "allreduce_calls", "allgather_calls", "unpack_allreduce_ms", "unpack_allreduce_calls", "gemm_3xtf32_ms")
 
 
 def ours_line(*, args, world, cfg_name, D, V, nnz, k, sha16, total_docs, dev_ms, e2e_s, h2d, d2h, st, state, clocks,
@@ -368,6 +368,8 @@ def ours_line(*, args, world, cfg_name, D, V, nnz, k, sha16, total_docs, dev_ms,
                 "ks_block_steps": st["ks_ops"], "ks_gs_third_passes_elided": st["ks_gs_elided"],
                 "spmm_head_words": int(st["spmm_head_words"]), "spmm_tail_nnz": int(st["spmm_tail_nnz"]),
                 "lloyd_iters": state["iters"], "nconv": state["nconv"], "ks_row_sharded": bool(st.get("ks_row_sharded", 0.0)),
+                # collectives carried by the library's own kernels over peer memory (coll.cu) instead of NCCL, per step
+                "p2p_collectives_per_step": state.get("p2p_collectives", 0.0) / max(args.steps, 1),
                 "options": list(getattr(args, "opt", []) or [])},
         # the e2e leg moves what the reference-side shim moves: A up (u64 row ids), zetas, all of B (vals, u64 rows,
         # offsets, original_cols), eigenvalues, U, seeds, projected centers and the lifted centers down
@@ -507,6 +509,10 @@ def bench_ours(args):
     sampler.mark_end()
     dev_ms = ms.value
     st = {n: ctx.stat(n) for n in STAT_NAMES}
+    try:
+        state["p2p_collectives"] = ctx.stat("p2p_collectives")
+    except Exception:       # single GPU, or the peer workspace could not be mapped: the counter does not exist
+        state["p2p_collectives"] = 0.0
     # ---- SURVEY 8(f) row 1, reported beside the metric (not part of it): Lloyd on the full-dimensional B from
     # the lifted centers the last step left on the device (trainer.cpp:566)
     ctx.call("isle_cuda_reset_stats")

@@ -1263,9 +1263,7 @@ struct KsState {
         reverse_top_kernel<<<(mm * kk + 255) / 256, 256, 0, c.stream>>>(Tm.p, Wev.p, mm, kk, S.p, theta.p);
         count_launch(c);
         // V_mid <- V[:, nconv:m) S ; new starts V[:, m:m+b) move to [k, k+b)
-        ISLE_CUBLAS_CHECK(cublasSgemm(c.cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, kk, mm, &one, Vcol(nconv), (int)n,
-                                      S.p, mm, &zero, Vtmp.p, (int)n));
-        count_launch(c);
+        gemm_3xtf32(c, (int)n, kk, mm, Vcol(nconv), (int)n, S.p, mm, Vtmp.p, (int)n);     // tensor cores above ~20 GFLOP
         ISLE_CUDA_CHECK(cudaMemcpyAsync(Vcol(nconv), Vtmp.p, (size_t)n * kk * 4, cudaMemcpyDeviceToDevice, c.stream));
         ISLE_CUDA_CHECK(cudaMemcpyAsync(Vcol(k), Vcol(m), (size_t)n * b * 4, cudaMemcpyDeviceToDevice, c.stream));
         // residual coupling block: H[m:m+b, m-b:m) S[mm-b:mm, :]  -> Htmp rows [0,b)

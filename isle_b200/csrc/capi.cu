@@ -738,7 +738,6 @@ int isle_cuda_cleanup_eigensolver(isle_cuda_ctx *h)
     return guarded_all(h, [&](Ctx &c) {
         c.U.release();
         c.P.release();
-        c.P_hi.release();
         c.P_lo.release();
         c.p_l2.release();
         c.have_U = c.have_P = false;

@@ -19,6 +19,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace isle {
 
@@ -34,144 +35,11 @@ namespace isle {
 // ---------------------------------------------------------------------------------------------------------------
 // peer-to-peer collectives
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kMaxPeers = 16;
-constexpr size_t kP2pFlagBytes = 4096;            // fa[16], fb[16] (u64, written by the peers), two local CTA counters
-constexpr size_t kP2pRegion = (size_t)8 << 20;    // stage / result area of the two-shot form
-constexpr size_t kP2pSlot = (size_t)64 << 10;     // one-shot message limit
-constexpr size_t kP2pOffStage = kP2pFlagBytes;
-constexpr size_t kP2pOffResult = kP2pOffStage + kP2pRegion;
-constexpr size_t kP2pOffSlots = kP2pOffResult + kP2pRegion;                 // [parity 2][src 16][2 * kP2pSlot]
-constexpr size_t kP2pBytes = kP2pOffSlots + 2 * kMaxPeers * (2 * kP2pSlot);   // flag-in-data words: 8 bytes per 4 of payload
-
-struct P2pArgs {
-    char *ws[kMaxPeers];
-    int me, world;
-    unsigned long long epoch;
-    unsigned tgt_a, tgt_b;
-    uint32_t *diag;
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-// bounded wait for `*flag >= epoch` (a peer that never arrives fails the launch instead of hanging the GPU)
-__device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigned long long epoch, uint32_t *diag, int what, int peer)
-{
-    for (long long spin = 0;; ++spin) {
-        if (ld_acquire_sys(flag) >= epoch) return;
-        if (spin > 64) __nanosleep(spin > 4096 ? 1000 : 50);
-        if (spin > 8000000) {           // ~8 s
-            if (diag) { diag[0] = 0xDEAD0000u | (uint32_t)what; diag[1] = (uint32_t)peer; diag[2] = (uint32_t)epoch; __threadfence_system(); }
-            __trap();
-        }
-    }
-}
-// all CTAs of this launch have finished the preceding phase -> tell every rank (flag index `which`: 0 = fa, 1 = fb)
-__device__ __forceinline__ void p2p_signal(const P2pArgs &a, int which, unsigned target)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        unsigned *cnt = reinterpret_cast<unsigned *>(a.ws[a.me] + 2 * kMaxPeers * 8) + which;
-        const unsigned old = atomicAdd(cnt, 1u);
-        if (old + 1u == target) {
-            __threadfence_system();
-            for (int r = 0; r < a.world; ++r)
-                st_release_sys(reinterpret_cast<unsigned long long *>(a.ws[r]) + which * kMaxPeers + a.me, a.epoch);
-        }
-    }
-}
-__device__ __forceinline__ void p2p_wait_all(const P2pArgs &a, int which)
-{
-    if ((int)threadIdx.x < a.world)
-        p2p_wait(reinterpret_cast<const unsigned long long *>(a.ws[a.me]) + which * kMaxPeers + threadIdx.x, a.epoch, a.diag, which,
-                 (int)threadIdx.x);
-    __syncthreads();
-}
-
-template <class T, int OP> struct Vec16;     // 16 bytes of T with the reduction OP (0 sum, 1 max)
-template <class T, int OP> struct Vec16 {
-    static constexpr int N = 16 / sizeof(T);
-    alignas(16) T v[N];
-    __device__ __forceinline__ static Vec16 load_cv(const void *p)
-    {
-        Vec16 r;
-        const uint4 u = __ldcv(reinterpret_cast<const uint4 *>(p));
-        *reinterpret_cast<uint4 *>(r.v) = u;
-        return r;
-    }
-    __device__ __forceinline__ static Vec16 load(const void *p)
-    {
-        Vec16 r;
-        *reinterpret_cast<uint4 *>(r.v) = *reinterpret_cast<const uint4 *>(p);
-        return r;
-    }
-    __device__ __forceinline__ void store(void *p) const { *reinterpret_cast<uint4 *>(p) = *reinterpret_cast<const uint4 *>(v); }
-    __device__ __forceinline__ void acc(const Vec16 &o)
-    {
-#pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = OP == 0 ? (T)(v[i] + o.v[i]) : (v[i] > o.v[i] ? v[i] : o.v[i]);
-    }
-};
-
-// buf (n elements, 16-byte aligned, nv = ceil(n * sizeof(T) / 16) vectors; the pad lanes of the last vector are zero in
-// every stage because the stage copy writes them so) -> element-wise reduction over the ranks, in place
 template <class T, int OP>
 __global__ void __launch_bounds__(512)
 p2p_allreduce2_kernel(P2pArgs a, T *__restrict__ buf, size_t n)
 {
-    typedef Vec16<T, OP> V;
-    const size_t nv = (n * sizeof(T) + 15) / 16;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-    char *mine = a.ws[a.me];
-    const bool al = (reinterpret_cast<uintptr_t>(buf) & 15) == 0;
-    // phase A: stage my vector where the peers can read it
-#pragma unroll 4
-    for (size_t i = tid; i < nv; i += nth) {
-        V x;
-        if (al && (i + 1) * V::N <= n) x = V::load(buf + i * V::N);
-        else {
-#pragma unroll
-            for (int j = 0; j < V::N; ++j) x.v[j] = (i * V::N + j < n) ? buf[i * V::N + j] : (T)0;
-        }
-        x.store(mine + kP2pOffStage + i * 16);
-    }
-    p2p_signal(a, 0, a.tgt_a);
-    p2p_wait_all(a, 0);
-    // phase B: my slice of the vectors, summed in rank order, stored into every rank's result area; the loads from all
-    // ranks are issued together (NVLink latency is paid once per vector, not once per rank)
-    const size_t per = (nv + a.world - 1) / a.world;
-    const size_t lo = per * a.me < nv ? per * a.me : nv, hi = lo + per < nv ? lo + per : nv;
-    for (size_t i = lo + tid; i < hi; i += nth) {
-        V x[kMaxPeers];
-#pragma unroll
-        for (int r = 0; r < kMaxPeers; ++r)
-            if (r < a.world) x[r] = V::load_cv(a.ws[r] + kP2pOffStage + i * 16);
-#pragma unroll
-        for (int r = 1; r < kMaxPeers; ++r)
-            if (r < a.world) x[0].acc(x[r]);
-#pragma unroll
-        for (int r = 0; r < kMaxPeers; ++r)
-            if (r < a.world) x[0].store(a.ws[r] + kP2pOffResult + i * 16);
-    }
-    p2p_signal(a, 1, a.tgt_b);
-    p2p_wait_all(a, 1);
-    // phase C: copy out
-#pragma unroll 4
-    for (size_t i = tid; i < nv; i += nth) {
-        const V x = V::load_cv(mine + kP2pOffResult + i * 16);
-        if (al && (i + 1) * V::N <= n) x.store(buf + i * V::N);
-        else
-            for (int j = 0; j < V::N; ++j)
-                if (i * V::N + j < n) buf[i * V::N + j] = x.v[j];
-    }
+    p2p_allreduce2_body<T, OP>(a, P2pCopyProducer<T, OP>{buf}, buf, n);
 }
 
 // One-shot form, flag-in-data (the "LL" idea): every 4-byte word of the payload travels as one 8-byte store {word, epoch},
@@ -231,6 +99,39 @@ p2p_allreduce1_kernel(P2pArgs a, T *__restrict__ buf, size_t n)
             s = r == 0 ? got.t : (OP == 0 ? (T)(s + got.t) : (s > got.t ? s : got.t));
         }
     buf[e] = s;
+}
+
+// all-gather of small pieces (count * sizeof(T) <= kP2pSlot), flag-in-data like the one-shot all-reduce: no barrier
+template <class T>
+__global__ void __launch_bounds__(256)
+p2p_allgather1_kernel(P2pArgs a, const T *__restrict__ send, T *__restrict__ recv, size_t count)
+{
+    constexpr int W = sizeof(T) / 4;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    const uint32_t flag = (uint32_t)a.epoch;
+    const size_t slots = kP2pOffSlots + ((size_t)(a.epoch & 1) * kMaxPeers) * (2 * kP2pSlot);
+    union { T t; uint32_t w[W]; } x;
+    x.t = send[e];
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+        for (int r = 0; r < a.world; ++r) st_ll(a.ws[r] + slots + (size_t)a.me * (2 * kP2pSlot) + (e * W + j) * 8, x.w[j], flag);
+    const char *in = a.ws[a.me] + slots + e * W * 8;
+    for (int r = 0; r < a.world; ++r) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            for (int spin = 0;; ++spin) {
+                const uint2 y = ld_ll(in + (size_t)r * (2 * kP2pSlot) + j * 8);
+                if (y.y == flag) { x.w[j] = y.x; break; }
+                if (spin > 64) __nanosleep(spin > 4096 ? 1000 : 50);
+                if (spin > 8000000) {
+                    if (a.diag) { a.diag[0] = 0xDEAD0003u; a.diag[1] = (uint32_t)r; a.diag[2] = flag; __threadfence_system(); }
+                    __trap();
+                }
+            }
+        }
+        recv[(size_t)r * count + e] = x.t;
+    }
 }
 
 // recv[r * count .. ) = send of rank r  (count floats per rank, world * count * 4 <= kP2pRegion): every rank stores its
@@ -347,6 +248,16 @@ static P2pArgs p2p_args(Ctx &c, unsigned grid, bool uses_a, bool uses_b)
     return a;
 }
 
+bool p2p_two_shot_begin(Ctx &c, size_t bytes, P2pArgs *args, unsigned *grid)
+{
+    if (c.world <= 1 || bytes == 0 || bytes > kP2pRegion || !p2p_ready(c)) return false;
+    // every CTA waits for all the others (grid-level phases): the grid must be co-resident, one CTA per SM at most
+    *grid = (unsigned)std::min<size_t>((size_t)c.num_sms, std::max<size_t>(4, bytes / 16 / 1024));
+    *args = p2p_args(c, *grid, true, true);
+    c.counters["p2p_collectives"] += 1.0;
+    return true;
+}
+
 template <class T, int OP>
 static bool p2p_allreduce(Ctx &c, T *buf, size_t n)
 {
@@ -356,10 +267,13 @@ static bool p2p_allreduce(Ctx &c, T *buf, size_t n)
         const P2pArgs a = p2p_args(c, 1, false, false);
         p2p_allreduce1_kernel<T, OP><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(a, buf, n);
     } else {
-        // every CTA waits for all the others (grid-level phases): the grid must be co-resident, one CTA per SM at most
-        const unsigned grid = (unsigned)std::min<size_t>((size_t)c.num_sms, std::max<size_t>(4, bytes / 16 / 1024));
-        const P2pArgs a = p2p_args(c, grid, true, true);
+        P2pArgs a;
+        unsigned grid = 0;
+        if (!p2p_two_shot_begin(c, bytes, &a, &grid)) return false;
         p2p_allreduce2_kernel<T, OP><<<grid, 512, 0, c.stream>>>(a, buf, n);
+        ISLE_CUDA_CHECK(cudaGetLastError());
+        count_launch(c);
+        return true;
     }
     ISLE_CUDA_CHECK(cudaGetLastError());
     count_launch(c);
@@ -372,6 +286,14 @@ static bool p2p_allgather(Ctx &c, const T *send, T *recv, size_t count)
 {
     const size_t bytes = count * sizeof(T) * (size_t)c.world;
     if (bytes > kP2pRegion || !p2p_ready(c)) return false;
+    if (count * sizeof(T) <= kP2pSlot) {
+        const P2pArgs a = p2p_args(c, 1, false, false);
+        p2p_allgather1_kernel<T><<<(unsigned)((count + 255) / 256), 256, 0, c.stream>>>(a, send, recv, count);
+        ISLE_CUDA_CHECK(cudaGetLastError());
+        count_launch(c);
+        c.counters["p2p_collectives"] += 1.0;
+        return true;
+    }
     const unsigned grid = (unsigned)std::min<size_t>(64, std::max<size_t>(1, bytes / 32768));
     const P2pArgs a = p2p_args(c, grid, true, true);
     p2p_allgather_kernel<T><<<grid, 256, 0, c.stream>>>(a, send, recv, count);
@@ -562,6 +484,7 @@ void allgather_f64(Ctx &c, const double *send, double *recv)
 }
 void bcast_f32(Ctx &c, float *, size_t, int) { need_nccl(c); }
 void p2p_destroy(Ctx &) {}
+bool p2p_two_shot_begin(Ctx &, size_t, P2pArgs *, unsigned *) { return false; }
 void selftest_collectives(Ctx &, unsigned long long *m, int *a) { *m = 0; *a = 0; }
 void allgather_f32(Ctx &c, const float *send, float *recv, size_t count)
 {

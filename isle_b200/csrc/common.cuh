@@ -248,7 +248,7 @@ struct Ctx {
     DevBuf<float> U;                       // V x k column-major
     uint64_t kp = 0;                       // padded projection width (multiple of 32)
     DevBuf<float> P;                       // DB x kp row-major, zero padded
-    DevBuf<float> P_hi, P_lo;              // split-TF32 copies of P for the tcgen05 engine (dist_tc.cu)
+    DevBuf<float> P_lo;                    // tf32(P - trunc_tf32(P)): the low part of the split-TF32 pair whose high part is P itself as the tensor core reads it (dist_tc.cu)
     DevBuf<float> p_l2;                    // DB
     DevBuf<float> catch_thr;               // k x V catchword thresholds of the last catchword_thresholds call (catchwords.cu)
     uint64_t catch_k = 0;
@@ -443,6 +443,8 @@ void download_doc_topic_sums(Ctx &c, uint32_t *docs, uint32_t *topics, float *su
 
 // ---- dist_tc.cu (tcgen05 split-TF32 distance contraction)
 void split_tf32(Ctx &c, const float *x, size_t n, float *hi, float *lo);
+void split_lo_trunc(Ctx &c, const float *x, size_t n, float *lo);
+void gemm_3xtf32(Ctx &c, int m, int n, int k, const float *A, int lda, const float *B, int ldb, float *C, int ldc);   // fp32-accurate GEMM on the tensor cores
 bool dist_tc_supported(const Ctx &c, uint32_t kp, uint32_t ncent);
 void dist_tc_launch(Ctx &c, const float *C, const float *c2, uint32_t ncent, int mode, uint32_t *assign, float *min_dist);
 

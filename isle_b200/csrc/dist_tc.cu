@@ -7,9 +7,12 @@
 // followed by cblas_isamin per document (src/sparseMatrix.cpp:1868-1870: argmin |x|, first index
 // on ties) or, for k-means++, min(min_dist, max(dist, 0)) (:2112-2126).
 //
-// 3xTF32: P = P_hi + P_lo and C = C_hi + C_lo with hi = tf32(x), lo = tf32(x - hi);
-// S = P_hi C_hi^T + P_hi C_lo^T + P_lo C_hi^T accumulated in fp32 in TMEM (the lo*lo term,
-// ~2^-22 relative, is dropped).  P is split once per projection, C once per pass.
+// 3xTF32: P = P_hi + P_lo and C = C_hi + C_lo; S = P_hi C_hi^T + P_hi C_lo^T + P_lo C_hi^T accumulated in fp32 in
+// TMEM (the lo*lo term, ~2^-22 relative, is dropped).  C is split once per pass into hi = tf32(x) (round to nearest) and
+// lo = tf32(x - hi).  P has NO hi copy: the tensor core reads a tf32 operand from the upper 19 bits of its 32-bit container
+// and ignores the rest, so the TMA tiles of P itself ARE P_hi = trunc_tf32(P); only P_lo = tf32(P - trunc_tf32(P)) (the
+// dropped 13 bits, rounded to tf32's 11: error 2^-22 of |P|, the same as the round-to-nearest split) is stored, once per
+// projection.  P is therefore held twice, not three times (2 x 8.4 GB per c3 shard instead of 3 x).
 //
 // Kernel shape (one persistent CTA per SM, 6 warps):
 //   warp 0 / lane 0   TMA producer: cp.async.bulk.tensor tiles of P_hi, P_lo (128 docs x 32 k) and
@@ -255,7 +258,28 @@ CUtensorMap make_map(const float *base, uint64_t rows, uint64_t kp, uint32_t box
     return m;
 }
 
+// lo = tf32(x - trunc_tf32(x)): the part of x the tensor core does not see when it reads x itself as a tf32 operand
+__global__ void split_lo_trunc_kernel(const float *__restrict__ x, size_t n, float *__restrict__ lo)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const float v = x[i];
+        const float r = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);     // exact
+        uint32_t l;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+        lo[i] = __uint_as_float(l);
+    }
+}
+
 }  // namespace
+
+void split_lo_trunc(Ctx &c, const float *x, size_t n, float *lo)
+{
+    if (!n) return;
+    split_lo_trunc_kernel<<<grid_for(n, 256, c.num_sms * 8), 256, 0, c.stream>>>(x, n, lo);
+    count_launch(c);
+}
 
 void split_tf32(Ctx &c, const float *x, size_t n, float *hi, float *lo)
 {
@@ -264,10 +288,38 @@ void split_tf32(Ctx &c, const float *x, size_t n, float *hi, float *lo)
     count_launch(c);
 }
 
+// C(m x n, ldc) = A(m x k, lda) B(k x n, ldb), column-major, with fp32 accuracy on the tensor cores: both operands are
+// split into hi = tf32(x), lo = tf32(x - hi) and three TF32 tensor-core GEMMs (cuBLAS: these are plain library GEMMs)
+// accumulate lo*hi, hi*lo, hi*hi in fp32, smallest terms first (products of tf32 numbers are exact in fp32; the dropped
+// lo*lo term is 2^-22 relative).  Used for the two dense contractions outside the hot loops that were fp32 FMA GEMMs:
+// the truncation product V S of block Krylov-Schur (restarted_block_ks.h:167) and the lift U C
+// (src/sparseMatrix.cpp:1446-1449); small products stay on the fp32 FMA path (dense_tc_min_flops).
+void gemm_3xtf32(Ctx &c, int m, int n, int k, const float *A, int lda, const float *B, int ldb, float *C, int ldc)
+{
+    const float one = 1.f, zero = 0.f;
+    const double flops = 2.0 * m * (double)n * k;
+    if (c.opt("dense_tc", 1) == 0 || flops < 1e6 * (double)c.opt("dense_tc_min_mflops", 20000)) {
+        ISLE_CUBLAS_CHECK(cublasSgemm(c.cublas, CUBLAS_OP_N, CUBLAS_OP_N, m, n, k, &one, A, lda, B, ldb, &zero, C, ldc));
+        count_launch(c);
+        return;
+    }
+    StatScope s(c, "gemm_3xtf32", 0.0, flops);
+    const size_t na = (size_t)lda * k, nb = (size_t)ldb * n;
+    DevBuf<float> ahi(na), alo(na), bhi(nb), blo(nb);
+    split_tf32(c, A, na, ahi.p, alo.p);
+    split_tf32(c, B, nb, bhi.p, blo.p);
+    const float *aa[3] = {alo.p, ahi.p, ahi.p}, *bb[3] = {bhi.p, blo.p, bhi.p};
+    for (int t = 0; t < 3; ++t) {
+        ISLE_CUBLAS_CHECK(cublasGemmEx(c.cublas, CUBLAS_OP_N, CUBLAS_OP_N, m, n, k, &one, aa[t], CUDA_R_32F, lda, bb[t], CUDA_R_32F, ldb,
+                                       t == 0 ? &zero : &one, C, CUDA_R_32F, ldc, CUBLAS_COMPUTE_32F_FAST_TF32, CUBLAS_GEMM_DEFAULT));
+        count_launch(c);
+    }
+}
+
 // The tensor-core engine needs whole 32-wide K blocks and at least one 16-wide center tile.
 bool dist_tc_supported(const Ctx &c, uint32_t kp, uint32_t ncent)
 {
-    return c.P_hi.p != nullptr && c.P_lo.p != nullptr && kp % BK == 0 && kp >= BK && ncent >= 1 && ncent <= 16384;
+    return c.P.p != nullptr && c.P_lo.p != nullptr && kp % BK == 0 && kp >= BK && ncent >= 1 && ncent <= 16384;
 }
 
 void dist_tc_launch(Ctx &c, const float *C, const float *c2, uint32_t ncent, int mode, uint32_t *assign, float *min_dist)
@@ -288,7 +340,7 @@ void dist_tc_launch(Ctx &c, const float *C, const float *c2, uint32_t ncent, int
     ISLE_REQUIRE(smem_bytes <= 227 * 1024, ISLE_ERR_ARG, "dist_tc: shared memory budget exceeded");
     ISLE_CUDA_CHECK(cudaFuncSetAttribute(dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
 
-    const CUtensorMap mp_hi = make_map(c.P_hi.p, DB, kp, BM), mp_lo = make_map(c.P_lo.p, DB, kp, BM);
+    const CUtensorMap mp_hi = make_map(c.P.p, DB, kp, BM), mp_lo = make_map(c.P_lo.p, DB, kp, BM);   // P itself is the hi operand
     const CUtensorMap mc_hi = make_map(chi.p, ncent, kp, BN), mc_lo = make_map(clo.p, ncent, kp, BN);
     Params p;
     p.d2 = c.p_l2.p; p.c2 = c2; p.assign = assign; p.min_dist = min_dist;

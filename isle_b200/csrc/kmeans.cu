@@ -114,12 +114,10 @@ void project(Ctx &c)
         }
     }
     if (c.opt("dist_kernel", 1) == 1 && DB) {
-        c.P_hi.alloc((size_t)DB * kp);
         c.P_lo.alloc((size_t)DB * kp);
-        StatScope s(c, "split_p", (double)DB * kp * 12.0);
-        split_tf32(c, c.P.p, (size_t)DB * kp, c.P_hi.p, c.P_lo.p);
+        StatScope s(c, "split_p", (double)DB * kp * 8.0);
+        split_lo_trunc(c, c.P.p, (size_t)DB * kp, c.P_lo.p);
     } else {
-        c.P_hi.release();
         c.P_lo.release();
     }
     ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
@@ -779,10 +777,8 @@ void lift_centers(Ctx &c, uint64_t ncols, const float *in, uint64_t ld_in, float
     c.lifted.alloc((size_t)V * ncols);
     c.lifted_cols = ncols;
     ISLE_CUDA_CHECK(cudaMemcpyAsync(din.p, in, din.bytes(), cudaMemcpyHostToDevice, c.stream));
-    const float one = 1.f, zero = 0.f;
-    ISLE_CUBLAS_CHECK(cublasSgemm(c.cublas, CUBLAS_OP_N, CUBLAS_OP_N, V, nc, k, &one, c.U.p, V, din.p, (int)ld_in, &zero,
-                                  c.lifted.p, V));
-    count_launch(c);
+    if ((size_t)ld_in * ncols > din.n) throw Error(ISLE_ERR_ARG, "lift_centers: bad ld_in");
+    gemm_3xtf32(c, V, nc, k, c.U.p, V, din.p, (int)ld_in, c.lifted.p, V);                     // tensor cores above ~20 GFLOP
     if (out) ISLE_CUDA_CHECK(cudaMemcpyAsync(out, c.lifted.p, c.lifted.bytes(), cudaMemcpyDeviceToHost, c.stream));
     ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }

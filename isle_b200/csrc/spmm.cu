@@ -21,6 +21,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace isle {
 
@@ -810,6 +811,43 @@ unpack_scaled_kernel(const float *__restrict__ T, uint32_t n, int b, const float
         if (j < b) Z[w + (size_t)j * ld] = (s * v[j]) * (colmax_bits ? col_pow2(colmax_bits[j], true) : 1.0f);
 }
 
+// The same fused with the all-reduce of the document-sharded operator (Z = sum over ranks of B_g (B_g^T X)): ONE
+// kernel un-permutes and scales this rank's T straight into the peer-visible stage area, and then reduces and redistributes
+// it over NVLink with plain peer loads / stores (p2p.cuh: rank r sums slice r of every rank's stage in rank order and
+// stores the sums into every rank's result area).  No NCCL call, no separate un-pack pass, no staging copy.
+struct UnpackProducer {
+    const float *T;
+    uint32_t n;
+    int b;
+    const float *scale;
+    const uint32_t *rank_of, *colmax_bits;
+    __device__ __forceinline__ void stage(char *stage_area, size_t nelem, size_t tid, size_t nth) const
+    {
+        float *Zs = reinterpret_cast<float *>(stage_area);
+        for (size_t w = tid; w < n; w += nth) {
+            const float s = scale ? scale[w] : 1.0f;
+            const float4 *t4 = reinterpret_cast<const float4 *>(T) + (size_t)rank_of[w] * 4;
+            float v[kStride];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 t = t4[q];
+                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+#pragma unroll
+            for (int j = 0; j < kStride; ++j)
+                if (j < b) Zs[w + (size_t)j * n] = (s * v[j]) * (colmax_bits ? col_pow2(colmax_bits[j], true) : 1.0f);
+        }
+        // pad lanes of the last 16-byte vector
+        const size_t padded = (nelem + 3) / 4 * 4;
+        for (size_t i = nelem + tid; i < padded; i += nth) Zs[i] = 0.f;
+    }
+};
+__global__ void __launch_bounds__(512)
+unpack_allreduce_kernel(P2pArgs a, UnpackProducer prod, float *__restrict__ Z, size_t nelem)
+{
+    p2p_allreduce2_body<float, 0>(a, prod, Z, nelem);
+}
+
 static void launch_gather(Ctx &c, int nch, bool add, const WorkItem *items, size_t n_items, const uint32_t *idx,
                           const float *in, float *out)
 {
@@ -987,6 +1025,18 @@ void spsptr_multiply_dev(Ctx &c, int b, const float *X, float *Z)
         } else {
             if (bfp) launch_gather_bfp(c, b, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybfp.p, c.zbuf.p);
             else launch_gather(c, nch, false, c.items_b.p, c.n_items_b, c.t2_idx.p, c.ybuf.p, c.zbuf.p);
+        }
+    }
+    if (c.world > 1 && c.opt("spmm_fused_allreduce", 1) != 0) {
+        P2pArgs a;
+        unsigned grid = 0;
+        if (p2p_two_shot_begin(c, (size_t)V * b * 4, &a, &grid)) {
+            StatScope s(c, "unpack_allreduce");
+            UnpackProducer prod{c.zbuf.p, V, b, c.sqrt_zeta.p, c.rank_of.p, bfp ? c.colmax.p : nullptr};
+            unpack_allreduce_kernel<<<grid, 512, 0, c.stream>>>(a, prod, Z, (size_t)V * b);
+            ISLE_CUDA_CHECK(cudaGetLastError());
+            count_launch(c);
+            return;
         }
     }
     unpack_scaled_kernel<<<(V + 255) / 256, 256, 0, c.stream>>>(c.zbuf.p, V, b, c.sqrt_zeta.p, c.rank_of.p,

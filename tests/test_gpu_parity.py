@@ -321,16 +321,17 @@ def test_panel_product_engines(ctx, engine, shape):
 @pytest.mark.parametrize("opts", [dict(ks_panel_tc=0, ks_panel_v2=0), dict(ks_panel_tc=0, ks_panel_v2=1), dict(ks_panel_tc=1),
                                   dict(ks_panel_tc=1, ks_gs_elide=0),
                                   dict(ks_panel_tc=0, ks_panel_v2=0, ks_custom_orth=0, ks_fast_qr=0),
-                                  dict(ks_panel_tc=1, ks_defer_rank=0), dict(ks_panel_tc=1, ks_force_qr_fallback=3)],
+                                  dict(ks_panel_tc=1, ks_defer_rank=0), dict(ks_panel_tc=1, ks_force_qr_fallback=3),
+                                  dict(ks_panel_tc=1, dense_tc_min_mflops=0)],
                          ids=["scalar-panels", "vector-panels", "tcgen05-panels", "tcgen05-panels-3-passes", "cublas-mgs",
-                              "rank-read-every-step", "forced-qr-fallback-and-redo"])
+                              "rank-read-every-step", "forced-qr-fallback-and-redo", "truncation-gemm-3xtf32"])
 def test_block_ks_engine_variants_c1(ctx, golden_c1, corpus_c1, opts):
     """Every panel / QR engine of the device solver meets the same bar against the reference's output."""
     g, c = golden_c1, corpus_c1
     vals, avg, nz = O.normalize_docs(c.counts, c.offsets)
     A, B, *_ = make_AB(ctx, c.V, c.D, c.k, vals, c.rows, c.offsets, avg, nz)
     defaults = dict(ks_panel_tc=1, ks_panel_v2=1, ks_custom_orth=1, ks_fast_qr=1, ks_gs_elide=1, ks_defer_rank=1,
-                    ks_force_qr_fallback=0)
+                    ks_force_qr_fallback=0, dense_tc_min_mflops=20000)
     try:
         for k_, v_ in {**defaults, **opts}.items():
             ctx.set_option(k_, v_)
@@ -395,6 +396,16 @@ def test_lloyd_matches_reference(ctx, golden_tiny, engine):
     assert abs(B.last_lloyd["objective"] - obj_ref) / obj_ref < 1e-4
     lifted = B.left_multiply_by_U_Spectra(C, k, k)
     assert np.max(np.abs(lifted - O.lift_centers(g["U_colmajor"].reshape(k, int(g["V"])).T, C))) < 1e-4
+    lift_ref = g["U_colmajor"].reshape(k, int(g["V"])).T.astype(np.float64) @ C.astype(np.float64).T
+    # the same product on the tensor cores (3xTF32 through three TF32 GEMMs, used for large products only by default):
+    # fp32-level agreement with the float64 product
+    try:
+        ctx.set_option("dense_tc_min_mflops", 0)
+        lifted_tc = B.left_multiply_by_U_Spectra(C, k, k)
+    finally:
+        ctx.set_option("dense_tc_min_mflops", 20000)
+    scale = np.max(np.abs(lift_ref))
+    assert np.max(np.abs(lifted_tc - lift_ref)) <= 2e-6 * scale and np.max(np.abs(lifted - lift_ref)) <= 2e-6 * scale
     ctx.set_option("dist_kernel", 1)
 
 
