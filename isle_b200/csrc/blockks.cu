@@ -851,7 +851,7 @@ struct KsState {
     bool defer_rank = true;
     int force_fallback = 0, fast_qr_calls = 0;
     DevBuf<float> F2;          // second operator-output buffer (deferred rank check)
-    int *h_rank = nullptr;     // pinned
+    int *h_rank = nullptr, *h_rank_dev = nullptr;     // host-mapped: written by the fast QR kernels, read after ev_rank
     cudaEvent_t ev_rank = nullptr;
     int lwork = 0;
     int qr_grid = 1;
@@ -914,7 +914,11 @@ struct KsState {
         defer_rank = c.opt("ks_defer_rank", 1) != 0;
         force_fallback = c.opt("ks_force_qr_fallback", 0);
         F2.alloc((size_t)n * b);
-        ISLE_CUDA_CHECK(cudaHostAlloc((void **)&h_rank, sizeof(int), cudaHostAllocDefault));
+        // the fast QR writes its rank straight into host-mapped memory: no D2H copy sits in the stream between the QR and
+        // the next operator application, so nothing waits on the copy engine (which a background download of B may be
+        // keeping busy: isle_cuda_download_B_begin)
+        ISLE_CUDA_CHECK(cudaHostAlloc((void **)&h_rank, sizeof(int), cudaHostAllocMapped));
+        ISLE_CUDA_CHECK(cudaHostGetDevicePointer((void **)&h_rank_dev, h_rank, 0));
         ISLE_CUDA_CHECK(cudaEventCreateWithFlags(&ev_rank, cudaEventDisableTiming));
         ISLE_CUDA_CHECK(cudaMemsetAsync(V.p, 0, V.bytes(), c.stream));
         ISLE_CUDA_CHECK(cudaMemsetAsync(H.p, 0, H.bytes(), c.stream));
@@ -996,7 +1000,7 @@ struct KsState {
     void qr_fast_launch(const float *Fsrc, int cols, float *Qdst)
     {
         CholQrParams q;
-        q.F = Fsrc; q.n = n; q.b = cols; q.Q = Qdst; q.R = Rb.p; q.rank_out = drank.p; q.part = cpart.p;
+        q.F = Fsrc; q.n = n; q.b = cols; q.Q = Qdst; q.R = Rb.p; q.rank_out = h_rank_dev; q.part = cpart.p;
         if (shard) {
             gram_rows_kernel<<<chol_grid, 256, kCholDynSmem, c.stream>>>(q, nullptr);
             sum_partials_kernel<<<1, 256, 0, c.stream>>>(cpart.p, (unsigned)chol_grid, gram1.p);
@@ -1012,7 +1016,6 @@ struct KsState {
                                                         kCholDynSmem, c.stream));
             count_launch(c);
         }
-        ISLE_CUDA_CHECK(cudaMemcpyAsync(h_rank, drank.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
         ISLE_CUDA_CHECK(cudaEventRecord(ev_rank, c.stream));
     }
     int qr_fast_result()
@@ -1257,8 +1260,7 @@ struct KsState {
                                              Wev.p, work.p, lwork, dinfo.p));
         count_launch(c);
         int info = 0;
-        ISLE_CUDA_CHECK(cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        read_small(c, &info, dinfo.p, sizeof(int));
         ISLE_REQUIRE(info == 0, ISLE_ERR_CUDA, "evd(H) failed");   // restarted_block_ks.h:156-157
         reverse_top_kernel<<<(mm * kk + 255) / 256, 256, 0, c.stream>>>(Tm.p, Wev.p, mm, kk, S.p, theta.p);
         count_launch(c);
@@ -1296,8 +1298,7 @@ struct KsState {
         std::vector<float> h((size_t)(b + 1) * k);
         // replicated ranks must take identical restart decisions: rank 0's numbers win
         if (c.world > 1) bcast_f32(c, pack.p, h.size(), 0);
-        ISLE_CUDA_CHECK(cudaMemcpyAsync(h.data(), pack.p, h.size() * 4, cudaMemcpyDeviceToHost, c.stream));
-        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        read_small(c, h.data(), pack.p, h.size() * 4);
         evs.assign(h.begin(), h.begin() + k);
         norms.resize(k);
         for (int j = 0; j < k; ++j) {

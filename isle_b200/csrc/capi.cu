@@ -382,6 +382,7 @@ void isle_cuda_destroy(isle_cuda_ctx *h)
     if (c.ev_fork) cudaEventDestroy(c.ev_fork);
     if (c.ev_join) cudaEventDestroy(c.ev_join);
     if (c.head_diag_host) cudaFreeHost(c.head_diag_host);
+    if (c.small_host) cudaFreeHost(c.small_host);
     if (c.cusolver) cusolverDnDestroy(c.cusolver);
     if (c.cublas) cublasDestroy(c.cublas);
     // device buffers are released by the DevBuf destructors inside Ctx

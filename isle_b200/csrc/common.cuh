@@ -277,6 +277,9 @@ struct Ctx {
     unsigned p2p_cnt_a = 0, p2p_cnt_b = 0; // cumulative CTA-arrival targets of the two grid-level counters
     uint32_t *p2p_diag_host = nullptr, *p2p_diag_dev = nullptr;   // host-mapped record of a timed-out wait
 
+    unsigned char *small_host = nullptr, *small_dev = nullptr;   // host-mapped landing zone of read_small()
+    bool small_failed = false;
+
     // ---- stats / options
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     bool profiling = false;
@@ -362,6 +365,7 @@ void sample_docs(Ctx &c, float sample_rate, uint64_t seed, uint8_t *select_out, 
 void download_B(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets, uint64_t *orig);
 void download_B_begin(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets, uint64_t *orig);
 void download_B_end(Ctx &c);
+void read_small(Ctx &c, void *dst, const void *dev_src, size_t bytes);   // synchronising small D2H read that bypasses the copy engine
 float frobenius(Ctx &c);
 
 // ---- ingest.cu (text -> entries -> CSC -> normalised A on the device)

@@ -521,8 +521,7 @@ void PanelTc::decide_elision(Ctx &c, float ratio)
 uint32_t PanelTc::elided(Ctx &c)
 {
     uint32_t v = 0;
-    ISLE_CUDA_CHECK(cudaMemcpyAsync(&v, flags.p + 3, 4, cudaMemcpyDeviceToHost, c.stream));
-    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    read_small(c, &v, flags.p + 3, 4);
     return v;
 }
 

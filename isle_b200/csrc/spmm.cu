@@ -110,8 +110,7 @@ static void build_items(Ctx &c, const int64_t *off, uint32_t nrows, DevBuf<WorkI
     DevBuf<uint8_t> tmp(tb);
     ISLE_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, scan.p, (int)(nrows + 1), c.stream));
     uint32_t total = 0;
-    ISLE_CUDA_CHECK(cudaMemcpyAsync(&total, scan.p + nrows, 4, cudaMemcpyDeviceToHost, c.stream));
-    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    read_small(c, &total, scan.p + nrows, 4);
     n_items = total;
     items.alloc(total);
     count_launch(c, 2);
@@ -326,8 +325,7 @@ void build_csr(Ctx &c, bool head_i8)
         count_ge_kernel<<<1, 1, 0, c.stream>>>(len_sorted.p, V, thr, dcnt.p);
         count_launch(c);
         uint32_t h0 = 0;
-        ISLE_CUDA_CHECK(cudaMemcpyAsync(&h0, dcnt.p, 4, cudaMemcpyDeviceToHost, c.stream));
-        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        read_small(c, &h0, dcnt.p, 4);
         const uint32_t hmax = (uint32_t)std::max(0, c.opt("spmm_head_max", 4096));
         H = std::min(h0, hmax) / kTileK * kTileK;
     }
@@ -345,8 +343,7 @@ void build_csr(Ctx &c, bool head_i8)
         scan_to_offsets(c, cnt.p, (size_t)DB + 1, c.t1_off.p);
     }
     int64_t nnz_tail = 0;
-    ISLE_CUDA_CHECK(cudaMemcpyAsync(&nnz_tail, c.t1_off.p + DB, 8, cudaMemcpyDeviceToHost, c.stream));
-    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    read_small(c, &nnz_tail, c.t1_off.p + DB, 8);
     c.nnz_tail = nnz_tail;
     c.t1_idx.alloc((size_t)nnz_tail);
     const size_t nbits = (size_t)c.DBpad * H / kHeadChunk;       // uint4 entries per bitmap

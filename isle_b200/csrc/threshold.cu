@@ -13,6 +13,8 @@
 
 #include <cmath>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace isle {
@@ -501,6 +503,39 @@ void download_B(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets, uint64_t 
 // (DMA from the copy engine; staged through the driver's bounce buffers when the caller's arrays are pageable, which is why
 // it is a thread and not just an async call), and download_B_end() joins it.  The caller's arrays must stay valid and
 // unread until then.  One download at a time; anything that rebuilds B ends a pending one first.
+// Small device -> host read that does NOT go through the copy engine: a kernel stores the bytes into host-mapped memory and
+// the host waits for the stream.  The copy engine serves queued copies in order, so while a background download of B
+// (below) is in flight an ordinary 4-byte cudaMemcpyAsync on the main stream would wait for all 0.8 GB of it; these reads
+// are the eigensolver's control flow (operator-layout sizes, residuals, cuSOLVER's info) and must not.
+__global__ void publish_kernel(const unsigned char *__restrict__ src, unsigned char *__restrict__ dst, size_t bytes)
+{
+    for (size_t i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+}
+void read_small(Ctx &c, void *dst, const void *dev_src, size_t bytes)
+{
+    constexpr size_t kCap = 1 << 20;
+    if (bytes == 0) return;
+    if (!c.small_host && !c.small_failed) {
+        if (cudaHostAlloc((void **)&c.small_host, kCap, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void **)&c.small_dev, c.small_host, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (c.small_host) cudaFreeHost(c.small_host);
+            c.small_host = nullptr;
+            c.small_failed = true;
+        }
+    }
+    if (!c.small_host || bytes > kCap) {
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToHost, c.stream));
+        ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        return;
+    }
+    publish_kernel<<<1, bytes >= 1024 ? 1024 : 64, 0, c.stream>>>((const unsigned char *)dev_src, c.small_dev, bytes);
+    ISLE_CUDA_CHECK(cudaGetLastError());
+    count_launch(c);
+    ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    std::memcpy(dst, c.small_host, bytes);
+}
+
 void download_B_begin(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets, uint64_t *orig)
 {
     ISLE_REQUIRE(c.have_B, ISLE_ERR_ARG, "download_B_begin: build_B first");
@@ -533,10 +568,18 @@ void download_B_begin(Ctx &c, float *vals, uint64_t *rows, int64_t *offsets, uin
         };
         chk(cudaSetDevice(c.device), "cudaSetDevice");
         chk(cudaStreamWaitEvent(c.copy_stream, c.ev_copy, 0), "cudaStreamWaitEvent");
-        if (vals && n) chk(cudaMemcpyAsync(vals, c.dl_vals.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c.copy_stream), "copy vals");
-        if (rows && n) chk(cudaMemcpyAsync(rows, c.dl_rows.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c.copy_stream), "copy rows");
-        if (offsets) chk(cudaMemcpyAsync(offsets, c.b_off.p, (DB + 1) * 8, cudaMemcpyDeviceToHost, c.copy_stream), "copy offsets");
-        if (orig && DB) chk(cudaMemcpyAsync(orig, c.dl_orig.p, DB * 8, cudaMemcpyDeviceToHost, c.copy_stream), "copy original_cols");
+        // 32 MB pieces: other copies (the final U of the eigensolver) get their turn between two pieces; the eigensolver's
+        // small control-flow reads do not use the copy engine at all (read_small)
+        auto copy = [&](void *dst, const void *src, size_t bytes, const char *what) {
+            constexpr size_t kPiece = (size_t)32 << 20;
+            for (size_t off = 0; off < bytes; off += kPiece)
+                chk(cudaMemcpyAsync((char *)dst + off, (const char *)src + off, std::min(kPiece, bytes - off), cudaMemcpyDeviceToHost,
+                                    c.copy_stream), what);
+        };
+        if (vals && n) copy(vals, c.dl_vals.p, (size_t)n * 4, "copy vals");
+        if (rows && n) copy(rows, c.dl_rows.p, (size_t)n * 8, "copy rows");
+        if (offsets) copy(offsets, c.b_off.p, (DB + 1) * 8, "copy offsets");
+        if (orig && DB) copy(orig, c.dl_orig.p, DB * 8, "copy original_cols");
         chk(cudaStreamSynchronize(c.copy_stream), "cudaStreamSynchronize(copy)");
     });
 }
