@@ -377,8 +377,10 @@ def ours_line(*, args, world, cfg_name, D, V, nnz, k, sha16, total_docs, dev_ms,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(st["launches"]),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "B^T X and B Y passes of the operator (spmm_head_kernel: tcgen05 dense head; "
-                                               "spmm_gather_bfp_kernel: tail)",
+        "roofline": {"bound": "hbm", "kernel": "B^T X and B Y passes of the operator (spmm_head_i8_kernel: dense head on tcgen05 "
+                                               "kind::i8, beside it spmm_gather_bfp_kernel: sparse tail; one pass = one launch of each)",
+                     "binds": "L2 -> SM fabric (one 32-byte operand row per nonzero: ~1.2 GB per pass at 7-8 TB/s), not HBM: "
+                              "profiles/r2_spmm_ncu_full.md",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
                      "traffic": traffic, "traffic_source": "stored ncu --set full capture (profiles/spmm_traffic.json), not measured in this run" if traffic else None,
                      "peak_source": peak_src, "launches": int(ncalls),

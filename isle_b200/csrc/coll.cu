@@ -7,7 +7,7 @@
 // redistributes with plain loads / stores through NVLink, synchronising the GPUs with release / acquire flags in the same
 // workspace -- no proxy thread, no ring, one launch.  Sums are formed in rank order by exactly one rank per element and
 // broadcast, so every rank receives bit-identical results (the replicated parts of the solver stay in lock step).
-//   <= 64 KB    one-shot: push my vector into slot [me] of every peer, one barrier, everybody adds the slots in rank order
+//   <= 256 KB   one-shot: push my vector into slot [me] of every peer, one barrier, everybody adds the slots in rank order
 //   <= 8 MB     two-shot: stage locally, barrier, rank r reduces slice r reading every peer's stage and stores the sums
 //               into every peer's result area, barrier, copy out
 //   larger      NCCL (the bins x V threshold histogram: bandwidth-bound, once per step); so is everything when the
@@ -263,7 +263,7 @@ static bool p2p_allreduce(Ctx &c, T *buf, size_t n)
 {
     const size_t bytes = n * sizeof(T);
     if (bytes > kP2pRegion || !p2p_ready(c)) return false;
-    if (bytes <= kP2pSlot) {
+    if (bytes <= kP2pOneShotMax) {
         const P2pArgs a = p2p_args(c, 1, false, false);
         p2p_allreduce1_kernel<T, OP><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(a, buf, n);
     } else {
@@ -363,7 +363,7 @@ void selftest_collectives(Ctx &c, unsigned long long *mismatches_out, int *p2p_a
     *p2p_active_out = 1;
     DevBuf<unsigned long long> dmis(1);
     ISLE_CUDA_CHECK(cudaMemsetAsync(dmis.p, 0, 8, c.stream));
-    const size_t sizes[] = {1, 3, 250, 4096, 16384, 16385, 100003, 1 << 20, (1 << 21) - 5};
+    const size_t sizes[] = {1, 3, 250, 4096, 16385, 65536, 65537, 100003, 1 << 20, (1 << 21) - 5};
     unsigned salt = 0;
     for (int rep = 0; rep < 3; ++rep)
         for (size_t n : sizes) {
@@ -376,7 +376,7 @@ void selftest_collectives(Ctx &c, unsigned long long *mismatches_out, int *p2p_a
             }
         }
     // all-gathers
-    for (size_t count : {(size_t)1, (size_t)77, (size_t)20000, (size_t)(kP2pRegion / 4 / c.world)}) {
+    for (size_t count : {(size_t)1, (size_t)77, (size_t)20000, std::min<size_t>(262144, kP2pRegion / 4 / c.world), (size_t)(kP2pRegion / 4 / c.world)}) {
         DevBuf<float> send(count), r1(count * c.world), r2(count * c.world);
         fill_pattern_kernel<float><<<grid_for(count, 256), 256, 0, c.stream>>>(send.p, count, (unsigned)c.rank, ++salt);
         if (!p2p_allgather(c, send.p, r1.p, count)) throw Error(ISLE_ERR_CUDA, "selftest: the peer-to-peer all-gather refused a message");
@@ -390,7 +390,7 @@ void selftest_collectives(Ctx &c, unsigned long long *mismatches_out, int *p2p_a
     cudaEvent_t e0, e1;
     ISLE_CUDA_CHECK(cudaEventCreate(&e0));
     ISLE_CUDA_CHECK(cudaEventCreate(&e1));
-    const struct { const char *name; size_t n; } cases[] = {{"4mb", (size_t)1 << 20}, {"50kb", 12800}, {"2kb", 512}};
+    const struct { const char *name; size_t n; } cases[] = {{"4mb", (size_t)1 << 20}, {"256kb", 65536}, {"50kb", 12800}, {"2kb", 512}};
     for (const auto &cs : cases) {
         DevBuf<float> x(cs.n);
         ISLE_CUDA_CHECK(cudaMemsetAsync(x.p, 0, cs.n * 4, c.stream));

@@ -11,7 +11,8 @@ namespace isle {
 constexpr int kMaxPeers = 16;
 constexpr size_t kP2pFlagBytes = 4096;            // fa[16], fb[16] (u64, written by the peers), two local CTA counters
 constexpr size_t kP2pRegion = (size_t)8 << 20;    // stage / result area of the two-shot form
-constexpr size_t kP2pSlot = (size_t)64 << 10;     // one-shot message limit
+constexpr size_t kP2pSlot = (size_t)1 << 20;      // payload capacity of a flag-in-data slot (all-gather pieces up to this size)
+constexpr size_t kP2pOneShotMax = (size_t)256 << 10;   // one-shot all-reduce up to this size (its traffic grows with the rank count)
 constexpr size_t kP2pOffStage = kP2pFlagBytes;
 constexpr size_t kP2pOffResult = kP2pOffStage + kP2pRegion;
 constexpr size_t kP2pOffSlots = kP2pOffResult + kP2pRegion;                 // [parity 2][src 16][2 * kP2pSlot]
@@ -50,16 +51,21 @@ __device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigne
 // all CTAs of this launch have finished the preceding phase -> tell every rank (flag index `which`: 0 = fa, 1 = fb)
 __device__ __forceinline__ void p2p_signal(const P2pArgs &a, int which, unsigned target)
 {
+    __shared__ int s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        __threadfence_system();                      // this CTA's stores (local and peer) are visible system-wide ...
         unsigned *cnt = reinterpret_cast<unsigned *>(a.ws[a.me] + 2 * kMaxPeers * 8) + which;
-        const unsigned old = atomicAdd(cnt, 1u);
-        if (old + 1u == target) {
-            __threadfence_system();
-            for (int r = 0; r < a.world; ++r)
-                st_release_sys(reinterpret_cast<unsigned long long *>(a.ws[r]) + which * kMaxPeers + a.me, a.epoch);
-        }
+        s_last = atomicAdd(cnt, 1u) + 1u == target;  // ... before it is counted
+    }
+    __syncthreads();
+    // the last CTA to arrive tells every rank, one thread per rank so that the NVLink round trips overlap (one thread
+    // issuing `world` release stores in a row paid ~2.5 us for each)
+    if (s_last && (int)threadIdx.x < a.world) {
+        __threadfence_system();
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long *>(a.ws[threadIdx.x]) + which * kMaxPeers + a.me),
+                     "l"(a.epoch)
+                     : "memory");
     }
 }
 __device__ __forceinline__ void p2p_wait_all(const P2pArgs &a, int which)

