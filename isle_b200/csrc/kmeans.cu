@@ -228,22 +228,33 @@ static constexpr int kSkinnyMax = 16;
 // centers) under the HBM rate.
 static constexpr int kSkinnyDocs = 4;
 
+// NC = 4, 8 or 16: the register tile and the transpose-reduce are sized to the batch (k-means++ adds 1 + sqrt(s - 5) centers
+// per round: at k = 100 eleven of the nineteen rounds bring at most 4, seven at most 8)
+template <int NC>
 __global__ void __launch_bounds__(256)
 pp_skinny_kernel(const float4 *__restrict__ P, const float *__restrict__ d2, uint32_t DB, uint32_t kp4,
                  const float4 *__restrict__ C, const float *__restrict__ c2, uint32_t ncent, float *__restrict__ min_dist)
 {
+    constexpr int LOG = NC == 16 ? 4 : NC == 8 ? 3 : 2;
     extern __shared__ float4 sC[];     // [ncent][kp4]
     for (uint32_t i = threadIdx.x; i < ncent * kp4; i += blockDim.x) sC[i] = C[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
     uint32_t d0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kSkinnyDocs;
     const uint32_t stride = ((gridDim.x * blockDim.x) >> 5) * kSkinnyDocs;
+    // transpose-reduce: NC partial sums per lane x 32 lanes -> every lane ends with the full sum of ONE center, chosen by
+    // its top LOG lane bits (halving exchanges over xor 16, 8, ..., then plain sums over the remaining offsets)
+    uint32_t myc = 0;
+#pragma unroll
+    for (int s_ = 0; s_ < LOG; ++s_)
+        if (lane & (16u >> s_)) myc += (uint32_t)(NC >> (s_ + 1));
+    const float myc2 = myc < ncent ? c2[myc] : 0.f;
     for (; d0 < DB; d0 += stride) {
-        float acc[kSkinnyDocs][kSkinnyMax];
+        float acc[kSkinnyDocs][NC];
 #pragma unroll
         for (int r = 0; r < kSkinnyDocs; ++r)
 #pragma unroll
-            for (int c = 0; c < kSkinnyMax; ++c) acc[r][c] = 0.f;
+            for (int c = 0; c < NC; ++c) acc[r][c] = 0.f;
         const float4 *rowp[kSkinnyDocs];
 #pragma unroll
         for (int r = 0; r < kSkinnyDocs; ++r) rowp[r] = P + (size_t)min(d0 + r, DB - 1) * kp4;   // clamp: tail rows re-read a valid one
@@ -252,7 +263,7 @@ pp_skinny_kernel(const float4 *__restrict__ P, const float *__restrict__ d2, uin
 #pragma unroll
             for (int r = 0; r < kSkinnyDocs; ++r) p[r] = __ldg(rowp[r] + col);
 #pragma unroll
-            for (int c = 0; c < kSkinnyMax; ++c) {
+            for (int c = 0; c < NC; ++c) {
                 if ((uint32_t)c < ncent) {
                     const float4 q = sC[(size_t)c * kp4 + col];
 #pragma unroll
@@ -261,36 +272,30 @@ pp_skinny_kernel(const float4 *__restrict__ P, const float *__restrict__ d2, uin
                 }
             }
         }
-        // transpose-reduce: 16 partial sums per lane x 32 lanes -> lane l ends with the full sum of center
-        // c(l) = bits 4..1 of l (8 + 4 + 2 + 1 + 1 = 16 shuffles per document instead of 16 x 5)
-        const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
-        const uint32_t myc = (b16 ? 8u : 0u) + (b8 ? 4u : 0u) + (b4 ? 2u : 0u) + (b2 ? 1u : 0u);
-        const float myc2 = myc < ncent ? c2[myc] : 0.f;
 #pragma unroll
         for (int r = 0; r < kSkinnyDocs; ++r) {
-            float v8[8], v4[4], v2[2];
+            float v[NC];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float keep = b16 ? acc[r][8 + j] : acc[r][j], send = b16 ? acc[r][j] : acc[r][8 + j];
-                v8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
+            for (int c = 0; c < NC; ++c) v[c] = acc[r][c];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float keep = b8 ? v8[4 + j] : v8[j], send = b8 ? v8[j] : v8[4 + j];
-                v4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
+            for (int s_ = 0; s_ < LOG; ++s_) {
+                const int w = NC >> (s_ + 1);
+                const uint32_t off = 16u >> s_;
+                const bool hi = lane & off;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const float keep = b4 ? v4[2 + j] : v4[j], send = b4 ? v4[j] : v4[2 + j];
-                v2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                for (int jj = 0; jj < w; ++jj) {
+                    const float keep = hi ? v[w + jj] : v[jj], send = hi ? v[jj] : v[w + jj];
+                    v[jj] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
             }
-            float v = (b2 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? v2[0] : v2[1], 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            float sum = v[0];
+#pragma unroll
+            for (uint32_t off = 16u >> LOG; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
             const uint32_t d = d0 + r;
             const float rd2 = d < DB ? d2[d] : 0.f;
-            float best = myc < ncent ? fmaxf(__fadd_rn(__fadd_rn(-2.0f * v, myc2), rd2), 0.0f) : FLT_MAX;
+            float best = myc < ncent ? fmaxf(__fadd_rn(__fadd_rn(-2.0f * sum, myc2), rd2), 0.0f) : FLT_MAX;
 #pragma unroll
-            for (int o = 16; o > 1; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+            for (uint32_t off = 16; off >= (32u >> LOG); off >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, off));
             if (lane == 0 && d < DB) min_dist[d] = fminf(min_dist[d], best);
         }
     }
@@ -325,10 +330,18 @@ static void distance_pass(Ctx &c, const float *C, const float *c2, uint32_t ncen
     StatScope s(c, mode == 0 ? (tc ? "dist_tc" : "dist_simt") : (tc ? "pp_dist_tc" : skinny ? "pp_dist_skinny" : "pp_dist_simt"),
                 (double)DB * kp * 4.0 + (double)DB * 8.0, 2.0 * (double)DB * ncent * (double)c.k);
     if (skinny) {
-        ISLE_CUDA_CHECK(cudaFuncSetAttribute(pp_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skinny_smem));
         const unsigned per_sm = skinny_smem > 100 * 1024 ? 1u : 2u;
-        pp_skinny_kernel<<<std::min<unsigned>((DB + 8 * kSkinnyDocs - 1) / (8 * kSkinnyDocs), (unsigned)c.num_sms * per_sm * 4), 256, skinny_smem, c.stream>>>(
-            reinterpret_cast<const float4 *>(c.P.p), c.p_l2.p, DB, kp / 4, reinterpret_cast<const float4 *>(C), c2, ncent, min_dist);
+        const unsigned grid = std::min<unsigned>((DB + 8 * kSkinnyDocs - 1) / (8 * kSkinnyDocs), (unsigned)c.num_sms * per_sm * 4);
+#define ISLE_SKINNY(NC)                                                                                                                  \
+    do {                                                                                                                                 \
+        ISLE_CUDA_CHECK(cudaFuncSetAttribute(pp_skinny_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skinny_smem));     \
+        pp_skinny_kernel<NC><<<grid, 256, skinny_smem, c.stream>>>(reinterpret_cast<const float4 *>(c.P.p), c.p_l2.p, DB, kp / 4,       \
+                                                                   reinterpret_cast<const float4 *>(C), c2, ncent, min_dist);          \
+    } while (0)
+        if (ncent <= 4) ISLE_SKINNY(4);
+        else if (ncent <= 8) ISLE_SKINNY(8);
+        else ISLE_SKINNY(16);
+#undef ISLE_SKINNY
         ISLE_CUDA_CHECK(cudaGetLastError());
         count_launch(c);
         return;

@@ -191,7 +191,7 @@ PP_ENGINES = {
 PP_DEFAULTS = dict(dist_kernel=1, pp_skinny=1, dist_tc_min_centers=17)
 
 
-@pytest.mark.parametrize("ncent", [1, 5, 16, 17, 40, 300])
+@pytest.mark.parametrize("ncent", [1, 4, 5, 8, 16, 17, 40, 300])
 @pytest.mark.parametrize("engine", list(PP_ENGINES))
 def test_c3m_min_dist_update_matches_oracle(ctx, golden_c3m, c3m, engine, ncent):
     """update_min_distsq_to_projected_centers (src/sparseMatrix.cpp:2075-2130) for a fixed batch of new centers:
