@@ -488,6 +488,7 @@ def bench_ours(args):
 
     sampler = ClockSampler(local)
     sampler.start()
+    barrier()       # ranks leave corpus generation (and rank 0 its TF32 peak measurement) seconds apart: start the library together
     # ---- warm-up: full end-to-end steps
     for i in range(args.warmup):
         upload()

@@ -76,15 +76,15 @@ p2p_allreduce1_kernel(P2pArgs a, T *__restrict__ buf, size_t n)
 #pragma unroll
     for (int j = 0; j < W; ++j) {
         unsigned pending = (1u << a.world) - 1u;
-        for (int spin = 0; pending; ++spin) {
+        P2pSpin sp;
+        while (pending) {
 #pragma unroll
             for (int r = 0; r < kMaxPeers; ++r)
                 if (pending >> r & 1u) {
                     const uint2 x = ld_ll(in + (size_t)r * (2 * kP2pSlot) + j * 8);
                     if (x.y == flag) { w[j][r] = x.x; pending &= ~(1u << r); }
                 }
-            if (spin > 64) __nanosleep(spin > 4096 ? 1000 : 50);
-            if (spin > 8000000) {
+            if (pending && sp.expired()) {
                 if (a.diag) { a.diag[0] = 0xDEAD0002u; a.diag[1] = pending; a.diag[2] = flag; __threadfence_system(); }
                 __trap();
             }
@@ -120,11 +120,11 @@ p2p_allgather1_kernel(P2pArgs a, const T *__restrict__ send, T *__restrict__ rec
     for (int r = 0; r < a.world; ++r) {
 #pragma unroll
         for (int j = 0; j < W; ++j) {
-            for (int spin = 0;; ++spin) {
+            P2pSpin sp;
+            for (;;) {
                 const uint2 y = ld_ll(in + (size_t)r * (2 * kP2pSlot) + j * 8);
                 if (y.y == flag) { x.w[j] = y.x; break; }
-                if (spin > 64) __nanosleep(spin > 4096 ? 1000 : 50);
-                if (spin > 8000000) {
+                if (sp.expired()) {
                     if (a.diag) { a.diag[0] = 0xDEAD0003u; a.diag[1] = (uint32_t)r; a.diag[2] = flag; __threadfence_system(); }
                     __trap();
                 }

@@ -36,13 +36,32 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// bounded wait for `*flag >= epoch` (a peer that never arrives fails the launch instead of hanging the GPU)
+// Back-off + time limit of every wait on a peer.  Ranks reach a collective seconds apart when their host sides differ
+// (corpus generation, rank 0's extra measurements), so the limit is generous: two minutes on %globaltimer, after which the
+// kernel records what it was waiting for and traps (a peer that never arrives fails the launch instead of hanging the GPU).
+constexpr unsigned long long kP2pTimeoutNs = 120ull * 1000ull * 1000ull * 1000ull;
+struct P2pSpin {
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    __device__ __forceinline__ bool expired()
+    {
+        ++spins;
+        if (spins <= 64) return false;
+        __nanosleep(spins > 4096 ? 1000 : 50);
+        if ((spins & 1023u) != 0) return false;
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t0 == 0) { t0 = t; return false; }
+        return t - t0 > kP2pTimeoutNs;
+    }
+};
+// bounded wait for `*flag >= epoch`
 __device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigned long long epoch, uint32_t *diag, int what, int peer)
 {
-    for (long long spin = 0;; ++spin) {
+    P2pSpin sp;
+    for (;;) {
         if (ld_acquire_sys(flag) >= epoch) return;
-        if (spin > 64) __nanosleep(spin > 4096 ? 1000 : 50);
-        if (spin > 8000000) {           // ~8 s
+        if (sp.expired()) {
             if (diag) { diag[0] = 0xDEAD0000u | (uint32_t)what; diag[1] = (uint32_t)peer; diag[2] = (uint32_t)epoch; __threadfence_system(); }
             __trap();
         }
