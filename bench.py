@@ -333,7 +333,7 @@ def bench_reference(args):
             core, wall, meta = run_ref_dump(c, cfg["k"], ncores, wd)
             times.append(core)
     line = reference_line(args, args.config, D_full, cfg["V"], nnz_full, cfg["k"], ncores, times, c.D, len(times), warm, same, note, sha16)
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------- our arm
@@ -609,14 +609,32 @@ def bench_ours(args):
             except Exception as e:  # the baseline is reported, never allowed to sink the bench line
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                                         "sample": f"unavailable: {e}"}
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def keep_stdout_for_the_line():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout at
+    init), so fd 1 is pointed at stderr for the run and the line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(text: str) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (text + "\n").encode())
+
+
 if __name__ == "__main__":
     a = parse()
+    keep_stdout_for_the_line()
     if a.impl == "reference":
         bench_reference(a)
     else:
