@@ -53,7 +53,7 @@ int isle_cuda_nccl_unique_id(void *id128);
  * arrays describe the whole corpus; the library cuts the documents into n contiguous ranges, runs on all GPUs at once
  * and returns per-document outputs (B, original_cols, assignments, (doc, topic) sums) stitched together in document
  * order, global outputs (zetas, eigenpairs, centers, thresholds, the model) from GPU 0.  Not available on it:
- * isle_cuda_sample_docs, isle_cuda_ingest_text, isle_cuda_upload_counts, isle_cuda_download_A. */
+ * isle_cuda_ingest_text, isle_cuda_upload_counts, isle_cuda_download_A. */
 int isle_cuda_create_multi(isle_cuda_ctx **ctx, int n_gpus, const int *devices);
 void isle_cuda_destroy(isle_cuda_ctx *ctx);
 const char *isle_cuda_last_error(const isle_cuda_ctx *ctx);
@@ -110,7 +110,10 @@ int isle_cuda_sampling_weights(isle_cuda_ctx *ctx, float *weights_out);
  * key_d = u_d^(1 / weight_d) (0 when the weight is 0) with u_d a counter-based uniform of (seed, d) in place of the
  * reference's racy libc rand(); select_out[d] = 1 for the documents whose key is at least the (floor(rate D) + 1)-th
  * largest (all of them when floor(rate D) >= D); *n_selected_out (may be NULL) = how many.  Pass select_out to
- * isle_cuda_build_B.  Single-GPU contexts. */
+ * isle_cuda_build_B.  In a sharded context D, rate D and the pivot are those of the WHOLE corpus (the uniforms are keyed by the
+ * global document number and the pivot comes from an exact distributed radix select), so the selection is bit-identical to
+ * the single-GPU one; select_out / *n_selected_out describe the rank's own documents.  A multi-GPU context returns the whole
+ * mask in document order. */
 int isle_cuda_sample_docs(isle_cuda_ctx *ctx, float sample_rate, uint64_t seed, uint8_t *select_out,
                           uint64_t *n_selected_out);
 /* Copies B back in the reference's layout for the host stages that follow the spectral

@@ -630,7 +630,20 @@ int isle_cuda_lloyd_full(isle_cuda_ctx *h, uint64_t k, float *centers_inout, int
 
 int isle_cuda_sample_docs(isle_cuda_ctx *h, float sample_rate, uint64_t seed, uint8_t *select_out, uint64_t *n_selected_out)
 {
-    if (h && h->g) { h->g->last_error = "sample_docs: single-GPU contexts only (the pivot is a corpus-wide order statistic)"; return ISLE_ERR_ARG; }
+    if (h && h->g) {      // every GPU selects among its own documents against the corpus-wide pivot; the masks are stitched in document order
+        Group &g = *h->g;
+        if (!select_out) { g.last_error = "sample_docs: bad arguments"; return ISLE_ERR_ARG; }
+        std::mutex mu;
+        uint64_t total = 0;
+        const int rc = g.run([&](int r, Ctx &c) {
+            uint64_t n = 0;
+            sample_docs(c, sample_rate, seed, select_out + g.d0[r], &n);
+            std::lock_guard<std::mutex> lk(mu);
+            total += n;
+        });
+        if (n_selected_out) *n_selected_out = total;
+        return rc;
+    }
     return guarded(h, [&](Ctx &c) { sample_docs(c, sample_rate, seed, select_out, n_selected_out); });
 }
 

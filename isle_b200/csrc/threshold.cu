@@ -16,6 +16,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "seg_select.cuh"
 
 namespace isle {
 
@@ -400,11 +401,12 @@ __device__ __forceinline__ uint64_t sample_mix64(uint64_t x)
 }
 
 __global__ void __launch_bounds__(256)
-sample_keys_kernel(const float *__restrict__ w, uint32_t D, uint64_t seed, float *__restrict__ key)
+sample_keys_kernel(const float *__restrict__ w, uint32_t D, uint64_t seed, uint64_t d_offset, float *__restrict__ key)
 {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
-    const float u = (float)(sample_mix64(seed ^ sample_mix64((uint64_t)d)) >> 40) * (1.0f / 16777216.0f);     // [0, 1), 24 bits
+    // d_offset + d = the document's number in the whole corpus (d_offset = 0 on a single GPU)
+    const float u = (float)(sample_mix64(seed ^ sample_mix64(d_offset + (uint64_t)d)) >> 40) * (1.0f / 16777216.0f);     // [0, 1), 24 bits
     const float wd = w[d];
     key[d] = wd == 0.0f ? 0.0f : powf(u, 1.0f / wd);
 }
@@ -420,32 +422,81 @@ sample_select_kernel(const float *__restrict__ key, uint32_t D, const float *__r
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_selected, (uint32_t)__popc(m));
 }
 
+__global__ void sample_pivot_kernel(const uint32_t *__restrict__ prefix, float *__restrict__ pivot)
+{
+    *pivot = segsel::unordered(prefix[0]);
+}
+
+// Document-sharded contexts: every rank holds a contiguous range of the documents.  The uniforms are keyed by the GLOBAL
+// document number (the ranks' document counts are all-gathered), so the keys are those of a single-GPU run on the whole
+// corpus; the pivot -- a corpus-wide order statistic -- comes from the exact distributed radix select of seg_select.cuh
+// (four rounds of one 256-bin histogram, all-reduced; no keys travel), so the selection is bit-identical to the
+// single-GPU one.  select_out / *n_selected_out describe the rank's own documents.
 void sample_docs(Ctx &c, float sample_rate, uint64_t seed, uint8_t *select_out, uint64_t *n_selected_out)
 {
     ISLE_REQUIRE(c.have_zeta, ISLE_ERR_ARG, "sample_docs: compute thresholds first");
     ISLE_REQUIRE(sample_rate >= 0.0f && select_out, ISLE_ERR_ARG, "sample_docs: bad arguments");
-    ISLE_REQUIRE(c.world == 1, ISLE_ERR_ARG, "sample_docs: single-GPU contexts only (the pivot is a global order statistic)");
     const uint32_t D = (uint32_t)c.D;
     if (n_selected_out) *n_selected_out = 0;
-    if (!D) return;
-    DevBuf<uint32_t> cnt(D), nsel(1);
-    DevBuf<float> w(D), key(D), sorted(D);
-    DevBuf<uint8_t> sel(D);
-    count_kept_kernel<<<grid_for((size_t)D * 32, 256, c.num_sms * 16), 256, 0, c.stream>>>(c.a_val.p, c.a_row.p, c.a_off.p, D, c.zeta.p,
-                                                                                      nullptr, cnt.p, w.p);
-    sample_keys_kernel<<<(D + 255) / 256, 256, 0, c.stream>>>(w.p, D, seed, key.p);
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortKeysDescending(nullptr, tb, key.p, sorted.p, (int)D, 0, 32, c.stream);
-    DevBuf<uint8_t> tmp(tb);
-    ISLE_CUDA_CHECK(cub::DeviceRadixSort::SortKeysDescending(tmp.p, tb, key.p, sorted.p, (int)D, 0, 32, c.stream));
-    // nth = (size_t)(sample_rate * (float)D)   (:1406)
-    const float nth_f = sample_rate * (float)D;
-    const uint32_t nth = nth_f >= (float)D ? D : (uint32_t)nth_f;
+    uint64_t d_offset = 0, D_total = D;
+    if (c.world > 1) {
+        DevBuf<unsigned long long> mine(1), all((size_t)c.world);
+        const unsigned long long dl = D;
+        ISLE_CUDA_CHECK(cudaMemcpyAsync(mine.p, &dl, 8, cudaMemcpyHostToDevice, c.stream));
+        allgather_u64(c, mine.p, all.p);
+        std::vector<unsigned long long> h((size_t)c.world);
+        read_small(c, h.data(), all.p, h.size() * 8);
+        D_total = 0;
+        for (int r = 0; r < c.world; ++r) { if (r < c.rank) d_offset += h[r]; D_total += h[r]; }
+    }
+    if (!D && c.world == 1) return;
+    const uint32_t Dn = std::max<uint32_t>(D, 1);
+    DevBuf<uint32_t> cnt(Dn), nsel(1);
+    DevBuf<float> w(Dn), key(Dn), sorted(Dn);
+    DevBuf<uint8_t> sel(Dn);
+    if (D) {
+        count_kept_kernel<<<grid_for((size_t)D * 32, 256, c.num_sms * 16), 256, 0, c.stream>>>(c.a_val.p, c.a_row.p, c.a_off.p, D, c.zeta.p,
+                                                                                          nullptr, cnt.p, w.p);
+        sample_keys_kernel<<<(D + 255) / 256, 256, 0, c.stream>>>(w.p, D, seed, d_offset, key.p);
+        count_launch(c, 2);
+    }
+    // nth = (size_t)(sample_rate * (float)D)   (:1406), D = the whole corpus
+    const float nth_f = sample_rate * (float)D_total;
+    const uint64_t nth64 = nth_f >= (float)D_total ? D_total : (uint64_t)nth_f;
     ISLE_CUDA_CHECK(cudaMemsetAsync(nsel.p, 0, 4, c.stream));
-    sample_select_kernel<<<(D + 255) / 256, 256, 0, c.stream>>>(key.p, D, sorted.p, nth, sel.p, nsel.p);
-    count_launch(c, 4);
+    if (c.world == 1) {
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortKeysDescending(nullptr, tb, key.p, sorted.p, (int)D, 0, 32, c.stream);
+        DevBuf<uint8_t> tmp(tb);
+        ISLE_CUDA_CHECK(cub::DeviceRadixSort::SortKeysDescending(tmp.p, tb, key.p, sorted.p, (int)D, 0, 32, c.stream));
+        const uint32_t nth = (uint32_t)nth64;
+        sample_select_kernel<<<(D + 255) / 256, 256, 0, c.stream>>>(key.p, D, sorted.p, nth, sel.p, nsel.p);
+        count_launch(c, 2);
+    } else {
+        ISLE_REQUIRE(D_total < 0xFFFFFFFFull, ISLE_ERR_RANGE, "sample_docs: more than 2^32 - 1 documents");
+        DevBuf<float> pivot(1);
+        if (nth64 < D_total) {
+            DevBuf<uint32_t> seg(Dn), kth(1), prefix(1), hist(256);
+            const uint32_t k0 = (uint32_t)nth64;
+            ISLE_CUDA_CHECK(cudaMemsetAsync(seg.p, 0, seg.bytes(), c.stream));
+            ISLE_CUDA_CHECK(cudaMemsetAsync(prefix.p, 0, 4, c.stream));
+            ISLE_CUDA_CHECK(cudaMemcpyAsync(kth.p, &k0, 4, cudaMemcpyHostToDevice, c.stream));
+            for (int round = 0; round < 4; ++round) {
+                ISLE_CUDA_CHECK(cudaMemsetAsync(hist.p, 0, hist.bytes(), c.stream));
+                if (D) segsel::hist_pairs_kernel<<<grid_for((size_t)D, 256), 256, 0, c.stream>>>(seg.p, key.p, (int64_t)D, prefix.p, round, hist.p);
+                allreduce_sum_u32(c, hist.p, 256);
+                segsel::pick_kernel<<<1, 128, 0, c.stream>>>(hist.p, 1, kth.p, prefix.p);
+                count_launch(c, 2);
+            }
+            sample_pivot_kernel<<<1, 1, 0, c.stream>>>(prefix.p, pivot.p);
+            count_launch(c);
+        }
+        // with nth >= D_total every document is kept (first operand of the test in the kernel: nth >= D)
+        if (D) sample_select_kernel<<<(D + 255) / 256, 256, 0, c.stream>>>(key.p, D, pivot.p, nth64 < D_total ? 0u : D, sel.p, nsel.p);
+        count_launch(c);
+    }
     uint32_t h = 0;
-    ISLE_CUDA_CHECK(cudaMemcpyAsync(select_out, sel.p, D, cudaMemcpyDeviceToHost, c.stream));
+    if (D) ISLE_CUDA_CHECK(cudaMemcpyAsync(select_out, sel.p, D, cudaMemcpyDeviceToHost, c.stream));
     ISLE_CUDA_CHECK(cudaMemcpyAsync(&h, nsel.p, 4, cudaMemcpyDeviceToHost, c.stream));
     ISLE_CUDA_CHECK(cudaStreamSynchronize(c.stream));
     if (n_selected_out) *n_selected_out = h;

@@ -120,7 +120,28 @@ def test_multi_gpu_context_matches_single_gpu_through_the_c_abi():
                     assign=B.last_lloyd["assign"], obj=B.last_lloyd["objective"], full_in=full_in, full=lifted,
                     full_assign=B.last_lloyd_full["assign"], thr=thr, cw=cw, model=model, dts=dts, seeds=seeds)
 
+    def sample(ctx):      # SURVEY 8(f) row 4 under sharding: same keys (global document numbers), corpus-wide pivot
+        from isle_b200._capi import ptr
+        import ctypes as C
+        A = SparseMatrix(c.V, c.D, ctx)
+        A.populate_normalized(vals, c.rows.astype(np.uint64), c.offsets, avg, nz)
+        A.compute_thresholds(0, c.V, None, c.k)
+        out = {}
+        for rate in (0.1, 0.37, 2.0):
+            sel, n = np.zeros(c.D, np.uint8), C.c_uint64()
+            ctx.call("isle_cuda_sample_docs", C.c_float(rate), 11, ptr(sel), C.byref(n))
+            assert int(sel.sum()) == n.value
+            out[rate] = sel
+        return out
+
     two = _capi.Context(n_gpus=2)
+    sel_two = sample(two)
+    one_ = _capi.Context(0)
+    sel_one = sample(one_)
+    one_.close()
+    for rate in sel_one:
+        assert np.array_equal(sel_two[rate], sel_one[rate]), rate
+    assert sel_one[2.0].all() and 0 < sel_one[0.1].sum() < 0.2 * c.D
     # the library's own collectives over peer memory (in one process: plain peer access) against NCCL, bit for bit
     import ctypes as C
     mism, active = C.c_uint64(), C.c_int()
