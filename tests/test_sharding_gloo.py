@@ -123,6 +123,76 @@ def test_sharded_host_logic_world2(tmp_path):
     assert sorted(out.keys()) == list(range(WORLD))
 
 
+def _ordered(x):
+    """seg_select.cuh ordered(): monotone map float32 -> uint32 (larger float, larger integer)."""
+    b = np.asarray(x, np.float32).view(np.uint32)
+    return np.where(b & 0x80000000, ~b, b | 0x80000000).astype(np.uint32)
+
+
+def _unordered(o):
+    o = np.uint32(o)
+    return np.array([o & 0x7FFFFFFF if o & 0x80000000 else ~o], np.uint32).view(np.float32)[0]
+
+
+def _radix_select_worker(rank, world, port, out):
+    """The exact distributed select of seg_select.cuh (stages G / H and the importance-sampling pivot under sharding): four
+    rounds of a 256-bin histogram of the next byte of ordered(x) over the values that still match the prefix, summed over
+    the ranks; no values travel.  Must return the (kth + 1)-th largest of the union, ties and signs included."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(7)                                   # same stream on every rank: everybody knows the union
+        parts = [np.concatenate([rng.standard_normal(5000).astype(np.float32), np.zeros(40, np.float32),
+                                 np.float32([1e-42, -1e-42, 3.5, 3.5, 3.5, -0.0]), rng.random(2000).astype(np.float32)])
+                 for _ in range(world)]
+        mine, union = parts[rank], np.sort(np.concatenate(parts))[::-1]
+        for kth in (0, 1, 17, 4999, len(union) // 2, len(union) - 1):
+            prefix, rem = np.uint32(0), kth
+            o = _ordered(mine)
+            for rnd in range(4):
+                match = np.ones(len(o), bool) if rnd == 0 else (o >> np.uint32(32 - 8 * rnd)) == prefix
+                h = torch.from_numpy(np.bincount((o[match] >> np.uint32(24 - 8 * rnd)) & 255, minlength=256).astype(np.int64))
+                dist.all_reduce(h)
+                h = h.numpy()
+                b = 255
+                while b > 0 and rem >= h[b]:
+                    rem -= int(h[b]); b -= 1
+                prefix = np.uint32((int(prefix) << 8) | b)
+            got = _unordered(prefix)
+            assert got == union[kth] or (got == 0 and union[kth] == 0), (kth, got, union[kth])
+        # importance sampling (isle_cuda_sample_docs under sharding): keys from GLOBAL document numbers, pivot = the
+        # (floor(rate D) + 1)-th largest key of the union -> the selection equals the single-process one
+        D = 9001
+        d0, d1 = sharding.shard_bounds(D, rank, world)
+        keys = np.random.default_rng(3).random(D).astype(np.float32) ** 3          # stand-in for u_d^(1 / w_d), keyed by global d
+        nth = int(np.float32(0.1) * np.float32(D))
+        pivot = np.sort(keys)[::-1][nth]
+        o, prefix, rem = _ordered(keys[d0:d1]), np.uint32(0), nth
+        for rnd in range(4):
+            match = np.ones(len(o), bool) if rnd == 0 else (o >> np.uint32(32 - 8 * rnd)) == prefix
+            h = torch.from_numpy(np.bincount((o[match] >> np.uint32(24 - 8 * rnd)) & 255, minlength=256).astype(np.int64))
+            dist.all_reduce(h)
+            h = h.numpy()
+            b = 255
+            while b > 0 and rem >= h[b]:
+                rem -= int(h[b]); b -= 1
+            prefix = np.uint32((int(prefix) << 8) | b)
+        assert _unordered(prefix) == pivot
+        sel = torch.tensor([int((keys[d0:d1] >= _unordered(prefix)).sum())])
+        dist.all_reduce(sel)
+        assert int(sel) == int((keys >= pivot).sum())
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_radix_select_world2():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_radix_select_worker, args=(WORLD, _free_port(), out), nprocs=WORLD, join=True)
+    assert sorted(out.keys()) == list(range(WORLD))
+
+
 def test_shard_bounds_cover_all_documents():
     for D in (0, 1, 7, 1500, 300000):
         for world in (1, 2, 3, 8):
