@@ -79,6 +79,9 @@ def test_c3m_oracle_pinned_at_large_k():
     B = O.to_csc(bv, br, bo, c.V)
     U = g["U_colmajor"].reshape(c.k, c.V).T
     P = O.project(B, U)
+    # the restated block Krylov-Schur at ncv = 650 (restarted_block_ks.h) against the reference's singular values
+    ev, _, nconv, _ = O.block_ks(B, c.k, seed=1)
+    assert nconv == c.k and np.max(np.abs(np.sqrt(ev) - np.sqrt(g["evalues"])) / np.sqrt(g["evalues"])) < 1e-4
     C0 = g["centers_lowd_init"].reshape(c.k, c.k)
     Cf, a, _ = O.run_lloyds(P, C0, 10)                       # ten Lloyd iterations from the reference's own seeds
     mism = np.nonzero(a != g["lloyd_assign"])[0]
