@@ -624,26 +624,10 @@ struct F2D {
     __host__ __device__ double operator()(float x) const { return (double)x; }
 };
 
-// For each local threshold t >= 0: first index i with cumul[i] > t  ==  upper_bound(dist_cumul, t) - 1
-// of the reference (:2187); the result is the GLOBAL column id + 1 (0 = not this rank's draw).
-__global__ void pick_kernel(const double *__restrict__ cumul, uint32_t n, const double *__restrict__ t, int nt,
-                            unsigned long long offset, unsigned long long *__restrict__ out)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nt) return;
-    const double tv = t[i];
-    if (tv < 0.0 || n == 0) { out[i] = 0ull; return; }
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (cumul[mid] > tv) hi = mid; else lo = mid + 1;
-    }
-    out[i] = offset + (lo < n ? lo : n - 1) + 1ull;
-}
-
-// The same with the draw itself on the device: thread i turns the uniform u[i] into the threshold total * u[i] (total = sum
-// of the ranks' partial totals, added in rank order as the host would), finds the rank whose share of the prefix sums holds
-// it (never an empty shard) and, on that rank, the document.  Saves the host round trip that fetched the totals.
+// D^2 sampling draw (src/sparseMatrix.cpp:2181-2199) on the device: thread i turns the uniform u[i] into the threshold
+// total * u[i] (total = sum of the ranks' partial totals, added in rank order), finds the rank whose share of the prefix sums
+// holds it (never an empty shard) and, on that rank, the first index with cumul[i] > t == upper_bound(dist_cumul, t) of the
+// reference (:2187); the result is the GLOBAL column id + 1 (0 = not this rank's draw).  One host read per round (the ids).
 struct PpDraws { double u[64]; };
 __global__ void pick_draws_kernel(const double *__restrict__ cumul, uint32_t n, const double *__restrict__ tot_all, int world, int rank,
                                   PpDraws dr, int nt, unsigned long long offset, unsigned long long *__restrict__ out)
@@ -690,7 +674,7 @@ void kmeanspp(Ctx &c, uint64_t k64, uint64_t seed, uint64_t *seeds_out, float *c
     std::mt19937_64 rng(seed);
     std::uniform_real_distribution<double> uni(0.0, 1.0);
     DevBuf<float> min_dist(std::max<uint32_t>(DB, 1)), cc((size_t)k * kp), c2(k), xch((size_t)kMaxDraw * kp);
-    DevBuf<double> cumul(std::max<uint32_t>(DB, 1)), dt(kMaxDraw), tot_mine(1), tot_all((size_t)c.world);
+    DevBuf<double> cumul(std::max<uint32_t>(DB, 1)), tot_mine(1), tot_all((size_t)c.world);
     DevBuf<uint32_t> cand(kMaxDraw);
     DevBuf<unsigned long long> gids(kMaxDraw);
     if (DB) {
@@ -724,7 +708,7 @@ void kmeanspp(Ctx &c, uint64_t k64, uint64_t seed, uint64_t *seeds_out, float *c
     add_centers({(uint64_t)(rng() % DBtot)});   // :2150 picks an arbitrary first doc
     int new_added = 1;
     double total = 0.0;
-    std::vector<double> totals((size_t)c.world), prefix((size_t)c.world + 1);
+    std::vector<double> totals((size_t)c.world);
     while (centers.size() < k) {
         StatScope s(c, "pp_round");
         const uint32_t first = (uint32_t)centers.size() - new_added;
